@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — BIC-scored DAGs/sec on the alarm-shaped config of BASELINE.json (configs[3]).
+
+Workload: a 37-variable / 46-edge network with random CPTs,
+10 M forward-sampled rows held as column-major uint8 in HBM (370 MB, replicated per GPU), and
+Erdos-Renyi candidate DAGs (m in [36, 92], in-degree <= 6) sharded over the GPUs.  One step =
+one fresh batch of 4096 candidate DAGs per GPU scored from a COLD family cache (the cache is
+cleared at the start of every step, so every step deduplicates its batch, counts every unique
+family over all 10 M rows and reduces it; nothing is carried over between steps).
+
+  value     DAGs/s with the candidate batch already resident in HBM
+  e2e       DAGs/s through the C ABI with HOST buffers (pinned adjacency in, scores out)
+  roofline  family-count kernels: algorithmic bytes ((k+1)*N + 4*q*r per family) / CUDA-event
+            time of those launches, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference
+            the CPU restatement of the reference path (oracle/bic_oracle.c, OpenMP over all host
+            cores; like the reference it recounts every family of every DAG) on a bounded sample
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torch.distributed.run.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n, edges, max in-degree of the truth, cardinalities, rows, candidate edges lo/hi, candidate in-degree cap
+    "alarm": dict(n=37, e=46, indeg=4, cards=[2, 3, 4], rows=10_000_000, m_lo=36, m_hi=92, cand_indeg=6,
+                  batch=4096, desc="alarm-shaped synthetic (37 vars, 46 edges, random CPTs), 10M rows"),
+    "synthetic_v12_c2": dict(n=12, e=20, indeg=4, cards=[2], rows=100_000, m_lo=11, m_hi=26, cand_indeg=None,
+                             batch=4096, desc="synthetic_v12_c2 (12 vars, 2 states), 100k rows"),
+}
+DATA_SEED = 20240
+CAND_SEED = 1234
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="alarm", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the row count (debug only)")
+    ap.add_argument("--batch", type=int, default=0, help="override DAGs per GPU per step (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_dataset_gpu(cfg, rows, device):
+    """Forward-sample the network on the GPU with torch (plumbing, not the product)."""
+    import torch
+    from dags_vae_search_b200 import synth
+    adj, card, cpts = synth.make_network(cfg["n"], cfg["e"], cfg["indeg"], cfg["cards"], DATA_SEED)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(DATA_SEED)
+    codes = torch.zeros((cfg["n"], rows), dtype=torch.uint8, device=device)
+    chunk = 1 << 22
+    for i in synth.topo_order(adj):
+        ps = np.flatnonzero(adj[:, i])
+        cum = torch.tensor(np.cumsum(cpts[i], axis=1)[:, :-1], dtype=torch.float64, device=device)
+        for s in range(0, rows, chunk):
+            m = min(chunk, rows - s)
+            j = torch.zeros(m, dtype=torch.int64, device=device)
+            for p in ps:
+                j = j * int(card[p]) + codes[p, s:s + m].long()
+            u = torch.rand(m, dtype=torch.float64, device=device, generator=gen)
+            codes[i, s:s + m] = (u[:, None] > cum[j]).sum(dim=1).to(torch.uint8)
+    return adj, card, codes
+
+
+def make_dataset_cpu(cfg, rows):
+    from dags_vae_search_b200 import synth
+    adj, card, cpts = synth.make_network(cfg["n"], cfg["e"], cfg["indeg"], cfg["cards"], DATA_SEED)
+    codes = synth.forward_sample(adj, card, cpts, rows, np.random.default_rng(DATA_SEED))
+    return adj, card, codes
+
+
+def candidate_batch(cfg, batch, step, rank, world):
+    from dags_vae_search_b200 import synth
+    return synth.er_candidates(cfg["n"], batch, cfg["m_lo"], cfg["m_hi"], cfg["cand_indeg"],
+                               seed=CAND_SEED + step * world + rank)
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(codes_host, card, adj_batch, target_seconds=12.0):
+    """DAGs/s of the CPU restatement (no family cache, like the reference) on a bounded sample."""
+    from oracle import c_oracle as C
+    threads = C.max_threads()
+    t0 = time.perf_counter()
+    C.score_dags_adj(codes_host, card, adj_batch[:2])
+    per_dag = (time.perf_counter() - t0) / 2
+    sample = int(max(2, min(len(adj_batch), target_seconds / max(per_dag, 1e-9))))
+    t0 = time.perf_counter()
+    C.score_dags_adj(codes_host, card, adj_batch[:sample])
+    dt = time.perf_counter() - t0
+    return sample / dt, threads, sample, dt
+
+
+def run_reference(args, cfg, rows, batch):
+    """--impl reference: the reference's own algorithm for the path (one full recount of all n
+    families per DAG, bnlearn.py:46-54 -> bnlearn_score.R:38) as restated in oracle/bic_oracle.c,
+    on every host core.  R/bnlearn are not installable here, so oracle/_ref does not exist."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle as C
+    try:   # same rows as the b200 arm when a GPU is there to generate them (data only)
+        import torch
+        assert torch.cuda.is_available()
+        _, card, codes_t = make_dataset_gpu(cfg, rows, torch.device("cuda", 0))
+        codes = codes_t.cpu().numpy()
+        del codes_t
+    except Exception:
+        _, card, codes = make_dataset_cpu(cfg, rows)
+    threads = C.max_threads()
+    adj0 = candidate_batch(cfg, batch, 0, 0, 1)
+    t0 = time.perf_counter()
+    C.score_dags_adj(codes, card, adj0[:2])
+    per_dag = (time.perf_counter() - t0) / 2
+    total_steps = args.steps + args.warmup
+    sample = int(max(1, min(batch, (150.0 / total_steps) / max(per_dag, 1e-9))))
+    times = []
+    for step in range(total_steps):
+        adj = candidate_batch(cfg, batch, step, 0, 1)[:sample]
+        t0 = time.perf_counter()
+        C.score_dags_adj(codes, card, adj)
+        if step >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    value = sample * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "BIC-scored DAGs/sec", "value": value, "unit": "DAGs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts + f64 reduce",
+        "data": "synthetic",
+        "config": {"workload": cfg["desc"], "rows": rows, "dags_per_step": sample, "cache": "none (reference recounts every family)"},
+        "cpu_baseline": {"value": value, "unit": "DAGs/s", "cores": threads, "kind": "port",
+                         "sample": f"first {sample} of {batch} candidate DAGs of each step, all {cfg['n']} families recounted per DAG"},
+        "e2e": {"value": value, "unit": "DAGs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    cfg = WORKLOADS[args.workload]
+    rows = args.rows or cfg["rows"]
+    batch = args.batch or cfg["batch"]
+    if args.impl == "reference":
+        run_reference(args, cfg, rows, batch)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dags_vae_search_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    true_adj, card, codes = make_dataset_gpu(cfg, rows, device)
+    scorer = pkg.BicScorer(codes, card, device=local_rank)
+    scorer.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = cfg["n"]
+
+    total_steps = args.warmup + args.steps
+    host_adj = [torch.from_numpy(candidate_batch(cfg, batch, s, rank, world)).pin_memory() for s in range(total_steps)]
+    dev_adj = [a.to(device) for a in host_adj]
+    dev_out = torch.empty(batch, dtype=torch.float64, device=device)
+    host_out = torch.empty(batch, dtype=torch.float64).pin_memory()
+
+    def step_resident(s):
+        scorer.cache_clear()
+        return scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
+
+    def step_e2e(s):
+        scorer.cache_clear()
+        return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False)
+
+    def timed(step_fn):
+        for s in range(args.warmup):
+            step_fn(s)
+        scorer.profile_enable(True)
+        scorer.profile_reset()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for s in range(args.warmup, total_steps):
+            step_fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if sampler else None
+        prof = scorer.profile()
+        scorer.profile_enable(False)
+        return float(ms.item()), prof, clocks
+
+    ms_res, prof, clocks = timed(step_resident)
+    checksum = float(dev_out.sum().item())
+    ms_e2e, prof_e2e, _ = timed(step_e2e)
+    assert not np.isnan(host_out.numpy()).any()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    dags = batch * world * args.steps
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = prof["alg_bytes"] / (prof["count_ms"] * 1e-3) / 1e9 if prof["count_ms"] > 0 else 0.0
+    line = {
+        "metric": "BIC-scored DAGs/sec", "value": dags / (ms_res * 1e-3), "unit": "DAGs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts + f64 reduce", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "rows": rows, "n": n, "dags_per_step_per_gpu": batch,
+                   "candidates": f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step",
+                   "cache": "family-score cache cleared at the start of every step (cold)",
+                   "l2": f"dataset {rows * n / 1e6:.0f} MB streamed per family; inputs larger than L2" if rows * n > 126e6 else "dataset fits L2",
+                   "parallelism": f"candidate-sharded x{world}, dataset replicated"},
+        "e2e": {"value": dags / (ms_e2e * 1e-3), "unit": "DAGs/s", "h2d_bytes_per_step": batch * n * n,
+                "d2h_bytes_per_step": batch * 8},
+        "gpu_launches": prof["kernel_launches"],
+        "family_count_rows_per_sec": prof["rows_counted"] / (prof["count_ms"] * 1e-3) if prof["count_ms"] > 0 else None,
+        "families_counted_per_step": prof["families_counted"] / args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_count (family count + fused fp64 reduce)",
+                     "launches": prof["count_launches"], "count_ms_per_step": prof["count_ms"] / args.steps,
+                     "peak_source": peak_src, "rank": 0},
+        "clocks": clocks,
+        "checksum": checksum,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        codes_host = codes.cpu().numpy()
+        rate, threads, sample, dt = cpu_oracle_rate(codes_host, card, host_adj[args.warmup].numpy())
+        line["cpu_baseline"] = {"value": rate, "unit": "DAGs/s", "cores": threads, "kind": "port",
+                                "sample": f"first {sample} candidate DAGs of one step ({dt:.1f} s), no family cache (reference recounts every family)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

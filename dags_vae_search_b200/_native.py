@@ -1,0 +1,119 @@
+"""ctypes binding of ``csrc/libbicgpu.so`` (C ABI: ``include/bicgpu.h``).
+
+The product path has no CPU fallback: if the CUDA library is missing or no B200 is visible,
+loading / context creation raises.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libbicgpu.so")
+
+BIC_OK = 0
+FLAG_DEVICE_PTRS = 1
+FLAG_NO_CYCLE_CHECK = 2
+FLAG_NO_CACHE = 4
+METRICS = {"bic": 0, "loglik": 1, "aic": 2}
+
+STATUS_NAMES = {
+    0: "BIC_OK", -1: "BIC_ERR_CUDA", -2: "BIC_ERR_ARG", -3: "BIC_ERR_NO_DATASET",
+    -4: "BIC_ERR_TABLE_TOO_LARGE", -5: "BIC_ERR_OOM", -6: "BIC_ERR_NCCL", -7: "BIC_ERR_BAD_CODE",
+    -8: "BIC_ERR_BAD_FAMILY",
+}
+
+# every symbol include/bicgpu.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_sync",
+    "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
+    "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
+    "bic_cache_stats", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
+    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy",
+]
+
+
+class BicError(Exception):
+    """Backend failure (the reference raises a bare ``Exception`` when its R child fails,
+    ``src/problem/bn/bnlearn.py:56-57``)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class CacheStats(ctypes.Structure):
+    _fields_ = [("families", ctypes.c_int64), ("capacity", ctypes.c_int64), ("lookups", ctypes.c_int64),
+                ("misses", ctypes.c_int64), ("bytes", ctypes.c_int64)]
+
+
+class Profile(ctypes.Structure):
+    _fields_ = [("count_ms", ctypes.c_double), ("count_launches", ctypes.c_int64),
+                ("kernel_launches", ctypes.c_int64), ("families_counted", ctypes.c_int64),
+                ("rows_counted", ctypes.c_int64), ("alg_bytes", ctypes.c_int64)]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/libbicgpu.so with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "bicgpu.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", CSRC] + (["-B"] if force else []) + ["libbicgpu.so"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            print(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("building libbicgpu.so failed")
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {CSRC}` (or __graft_entry__.build()). "
+            "dags_vae_search_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    L.bic_version.restype = ctypes.c_int
+    L.bic_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    L.bic_destroy.argtypes = [vp]
+    L.bic_last_error.argtypes = [vp]
+    L.bic_last_error.restype = ctypes.c_char_p
+    L.bic_set_stream.argtypes = [vp, vp]
+    L.bic_sync.argtypes = [vp]
+    L.bic_set_dataset.argtypes = [vp, vp, i64, i32, i64, vp, ctypes.c_int]
+    L.bic_count_families.argtypes = [vp, vp, vp, vp, i64, vp, vp, ctypes.c_int]
+    L.bic_score_families.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.c_int]
+    L.bic_score_dags_adj.argtypes = [vp, vp, i64, ctypes.c_int, vp, ctypes.POINTER(i64), ctypes.c_int]
+    L.bic_score_dags_csr.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp, ctypes.POINTER(i64), ctypes.c_int]
+    L.bic_score_dags_wire.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp, ctypes.POINTER(i64), ctypes.c_int]
+    L.bic_cache_clear.argtypes = [vp]
+    L.bic_cache_reserve.argtypes = [vp, i64]
+    L.bic_cache_stats.argtypes = [vp, ctypes.POINTER(CacheStats)]
+    L.bic_profile_enable.argtypes = [vp, ctypes.c_int]
+    L.bic_profile_reset.argtypes = [vp]
+    L.bic_profile_get.argtypes = [vp, ctypes.POINTER(Profile)]
+    L.bic_comm_unique_id.argtypes = [vp]
+    L.bic_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    L.bic_comm_destroy.argtypes = [vp]
+    for name in SYMBOLS:
+        if name not in ("bic_last_error",):
+            getattr(L, name).restype = ctypes.c_int
+    _LIB = L
+    return L
+
+
+def check(ctx, status: int) -> None:
+    if status != BIC_OK:
+        msg = lib().bic_last_error(ctx)
+        raise BicError(status, msg.decode() if msg else "")

@@ -1,0 +1,822 @@
+// libbicgpu.so — host side of the C ABI declared in include/bicgpu.h.
+//
+// Drop-in for the reference's per-DAG Rscript child (bnlearn.py:46-61 ->
+// bnlearn_score.R:7-40).  The context owns: the padded column-major uint8 dataset in HBM, the
+// family-score cache (open-addressing table + registry of keys / log-likelihoods), per-batch
+// workspace and a pinned header the kernels report through.  There is no CPU fallback: every
+// score comes from the kernels in count_kernels.cuh.
+#include "../../include/bicgpu.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cache_kernels.cuh"
+#include "common.cuh"
+#include "count_kernels.cuh"
+
+using namespace bic;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---- NCCL through dlopen: single-GPU users never need the library -------------------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_uid *) = nullptr;
+    int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(nccl_uid *))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(nccl_comm *, int, nccl_uid, int))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (int (*)(nccl_comm))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+            err = "libnccl lacks a required symbol";
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+constexpr int NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_SUM = 0;   // nccl.h: ncclDataType_t / ncclRedOp_t
+
+}  // namespace
+
+struct bic_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    int sm_count = 148;
+
+    // dataset
+    uint8_t *data = nullptr;
+    long long N = 0, stride = 0, N_total = 0;
+    int n = 0, W64 = 0, Wk = 0;
+    int *d_card = nullptr;
+    std::vector<int> card;
+
+    // family-score cache
+    u32 *table = nullptr;
+    u64 table_cap = 0;
+    u64 *regkeys = nullptr;
+    double *reg_ll = nullptr, *reg_np = nullptr;
+    long long reg_cap = 0, reg_count = 0;
+    long long lookups = 0, misses = 0;
+
+    // per-sub-batch workspace
+    DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
+    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll;
+    Header *d_hdr = nullptr, *h_hdr = nullptr;
+
+    // profiling
+    bool prof_on = false;
+    bic_profile_t prof = {};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_used;
+
+    // row sharding
+    nccl_comm comm = nullptr;
+    int rank_id = 0, world = 1;
+    bool ntotal_dirty = true;
+};
+
+namespace {
+
+int fail(bic_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? BIC_ERR_OOM : BIC_ERR_CUDA,           \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+
+#define TRY(call)                         \
+    do {                                  \
+        int rc_ = (call);                 \
+        if (rc_ != BIC_OK) return rc_;    \
+    } while (0)
+
+inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+#define LAUNCH(c) (++(c)->prof.kernel_launches)
+
+// Exclusive scan of `in[0..n)` into `out`, total written to *total (device).
+template <typename TI, typename TO>
+int scan_excl(bic_ctx *c, const TI *in, long long n, TO *out, TO *total, DevBuf &bsum) {
+    int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    if (nb < 1) nb = 1;
+    CU(bsum.ensure((size_t)nb * sizeof(TO)));
+    k_scan_partial<TI, TO><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bsum.as<TO>()); LAUNCH(c);
+    k_scan_bsums<TO><<<1, 1024, 0, c->stream>>>(bsum.as<TO>(), nb, total); LAUNCH(c);
+    k_scan_apply<TI, TO><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bsum.as<TO>(), out); LAUNCH(c);
+    CU(cudaGetLastError());
+    return BIC_OK;
+}
+
+void cache_free(bic_ctx *c) {
+    if (c->table) cudaFree(c->table);
+    if (c->regkeys) cudaFree(c->regkeys);
+    if (c->reg_ll) cudaFree(c->reg_ll);
+    if (c->reg_np) cudaFree(c->reg_np);
+    c->table = nullptr; c->regkeys = nullptr; c->reg_ll = nullptr; c->reg_np = nullptr;
+    c->table_cap = 0; c->reg_cap = 0; c->reg_count = 0;
+}
+
+// Make room for `extra` more families (worst case: every instance of a sub-batch is new).
+// Load factor stays <= 0.5; growth re-inserts the registry ids into a fresh table.
+int cache_ensure(bic_ctx *c, long long extra) {
+    long long want = c->reg_count + extra;
+    if (c->table && want <= c->reg_cap) return BIC_OK;
+    u64 cap = 1ull << 16;
+    while ((long long)(cap / 2) < want) cap <<= 1;
+    if (cap > (1ull << 30)) return fail(c, BIC_ERR_OOM, "family cache would exceed 2^30 slots; call bic_cache_clear()");
+    long long rcap = (long long)(cap / 2);
+    u32 *ntable = nullptr; u64 *nkeys = nullptr; double *nll = nullptr, *nnp = nullptr;
+    CU(cudaMalloc(&ntable, cap * sizeof(u32)));
+    CU(cudaMalloc(&nkeys, (size_t)rcap * c->Wk * sizeof(u64)));
+    CU(cudaMalloc(&nll, (size_t)rcap * sizeof(double)));
+    CU(cudaMalloc(&nnp, (size_t)rcap * sizeof(double)));
+    CU(cudaMemsetAsync(ntable, 0, cap * sizeof(u32), c->stream));
+    if (c->reg_count) {
+        CU(cudaMemcpyAsync(nkeys, c->regkeys, (size_t)c->reg_count * c->Wk * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nll, c->reg_ll, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nnp, c->reg_np, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        k_rehash<<<nblk(c->reg_count, 256), 256, 0, c->stream>>>(nkeys, c->Wk, c->reg_count, ntable, (u32)(cap - 1)); LAUNCH(c);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    long long keep = c->reg_count;
+    cache_free(c);
+    c->table = ntable; c->regkeys = nkeys; c->reg_ll = nll; c->reg_np = nnp;
+    c->table_cap = cap; c->reg_cap = rcap; c->reg_count = keep;
+    return BIC_OK;
+}
+
+int cache_clear(bic_ctx *c) {
+    if (c->table) CU(cudaMemsetAsync(c->table, 0, c->table_cap * sizeof(u32), c->stream));
+    c->reg_count = 0;
+    c->lookups = 0;
+    c->misses = 0;
+    return BIC_OK;
+}
+
+double metric_penalty(bic_ctx *c, int metric) {
+    if (metric == BIC_METRIC_BIC) return c->N_total > 0 ? 0.5 * log((double)c->N_total) : 0.0;
+    if (metric == BIC_METRIC_AIC) return 1.0;
+    return 0.0;
+}
+
+int header_reset(bic_ctx *c) {
+    CU(cudaMemsetAsync(c->d_hdr, 0, sizeof(Header), c->stream));
+    return BIC_OK;
+}
+
+int header_fetch(bic_ctx *c) {
+    CU(cudaMemcpyAsync(c->h_hdr, c->d_hdr, sizeof(Header), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BIC_OK;
+}
+
+template <int THREADS, bool GLOBAL>
+int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
+    static bool attr_set = false;   // one flag per template instance
+    if (smem > 48 * 1024 && !attr_set) {
+        CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_count<THREADS, GLOBAL><<<(unsigned)items, THREADS, smem, c->stream>>>(a); LAUNCH(c);
+    CU(cudaGetLastError());
+    ++c->prof.count_launches;
+    return BIC_OK;
+}
+
+// Row count over all ranks (ln N of the penalty) when the rows are sharded.
+int refresh_ntotal(bic_ctx *c) {
+    if (!c->ntotal_dirty) return BIC_OK;
+    c->N_total = c->N;
+    if (c->comm) {
+        long long *d = nullptr;
+        CU(cudaMalloc(&d, sizeof(long long)));
+        CU(cudaMemcpyAsync(d, &c->N, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        int rc = g_nccl.AllReduce(d, d, 1, NCCL_INT64, NCCL_SUM, c->comm, c->stream);
+        if (rc != 0) { cudaFree(d); return fail(c, BIC_ERR_NCCL, std::string("ncclAllReduce(N): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); }
+        CU(cudaMemcpyAsync(&c->N_total, d, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    }
+    c->ntotal_dirty = false;
+    return BIC_OK;
+}
+
+// Count (and reduce) `njobs` families described in c->cells_arr / c->class_jobs; the header in
+// pinned memory holds the class counts.  keys/key_base select registry or key buffer.
+int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, long long max_jobs,
+              double *ll_out, double *np_out, bool want_tables) {
+    const Header &h = *c->h_hdr;
+    const bool sharded = c->comm != nullptr;
+    const bool all_tables = want_tables || sharded;
+
+    // slices per family: enough CTAs to fill the GPU, but at least 64K rows per slice
+    NeedArgs na;
+    na.all = all_tables ? 1 : 0;
+    const long long target = (long long)c->sm_count * 8;
+    const long long smax = std::max<long long>(1, c->N / 65536);
+    bool any_table = all_tables;
+    for (int k = 0; k < NCLASS; ++k) {
+        long long cnt = h.class_count[k];
+        long long S = cnt ? std::min(smax, (target + cnt - 1) / cnt) : 1;
+        na.S[k] = (int)std::max<long long>(1, S);
+        if (cnt && (na.S[k] > 1 || k == 3)) any_table = true;
+    }
+
+    if (any_table) {
+        CU(c->need.ensure((size_t)njobs * sizeof(u32)));
+        CU(c->table_off.ensure((size_t)njobs * sizeof(u64)));
+        k_table_need<<<nblk(njobs, 256), 256, 0, c->stream>>>(c->cells_arr.as<u32>(), (u32)njobs, na, c->need.as<u32>()); LAUNCH(c);
+        TRY((scan_excl<u32, u64>(c, c->need.as<u32>(), njobs, c->table_off.as<u64>(), &c->d_hdr->table_cells, c->bsum64)));
+        TRY(header_fetch(c));
+        size_t cells = (size_t)c->h_hdr->table_cells;
+        CU(c->arena.ensure(std::max<size_t>(cells, 1) * sizeof(u32)));
+        CU(cudaMemsetAsync(c->arena.p, 0, std::max<size_t>(cells, 1) * sizeof(u32), c->stream));
+    }
+    CU(c->done.ensure((size_t)njobs * sizeof(u32)));
+    CU(cudaMemsetAsync(c->done.p, 0, (size_t)njobs * sizeof(u32), c->stream));
+
+    CountArgs a;
+    a.data = c->data; a.N = c->N; a.stride = c->stride; a.card = c->d_card; a.W64 = c->W64;
+    a.keys = keys; a.key_base = key_base;
+    a.arena = c->arena.as<u32>();
+    a.need = any_table ? c->need.as<u32>() : nullptr;
+    a.table_off = any_table ? c->table_off.as<u64>() : nullptr;
+    a.done = c->done.as<u32>();
+    a.ll_out = ll_out; a.np_out = np_out;
+    a.reduce = sharded ? 0 : 1;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->prof_on) {
+        if (c->ev_pool.empty()) {
+            CU(cudaEventCreate(&e0));
+            CU(cudaEventCreate(&e1));
+        } else {
+            e0 = c->ev_pool.back().first; e1 = c->ev_pool.back().second;
+            c->ev_pool.pop_back();
+        }
+        CU(cudaEventRecord(e0, c->stream));
+    }
+    for (int k = 0; k < NCLASS; ++k) {
+        long long cnt = h.class_count[k];
+        if (!cnt) continue;
+        a.jobs = c->class_jobs.as<int>() + (long long)k * max_jobs;
+        a.S = na.S[k];
+        long long items = cnt * a.S;
+        if (items > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
+        if (k == 0) TRY((launch_count<256, false>(c, a, items, CLASS0_CELLS * sizeof(u32))));
+        if (k == 1) TRY((launch_count<512, false>(c, a, items, CLASS1_CELLS * sizeof(u32))));
+        if (k == 2) TRY((launch_count<512, false>(c, a, items, CLASS2_CELLS * sizeof(u32))));
+        if (k == 3) TRY((launch_count<256, true>(c, a, items, 0)));
+    }
+    if (c->prof_on) {
+        CU(cudaEventRecord(e1, c->stream));
+        c->ev_used.push_back({e0, e1});
+    }
+    c->prof.families_counted += njobs;
+    c->prof.rows_counted += njobs * c->N;
+    c->prof.alg_bytes += (long long)h.alg_bytes;
+
+    if (sharded) {
+        size_t cells = (size_t)c->h_hdr->table_cells;
+        if (cells) {
+            int rc = g_nccl.AllReduce(c->arena.p, c->arena.p, cells, NCCL_UINT32, NCCL_SUM, c->comm, c->stream);
+            if (rc != 0) return fail(c, BIC_ERR_NCCL, std::string("ncclAllReduce(count tables): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        }
+        k_reduce_tables<256><<<(unsigned)njobs, 256, 0, c->stream>>>(a, (int)njobs); LAUNCH(c);
+        CU(cudaGetLastError());
+    }
+    return BIC_OK;
+}
+
+int check_header_err(bic_ctx *c) {
+    u32 e = c->h_hdr->err;
+    if (e & 2u) return fail(c, BIC_ERR_BAD_FAMILY, "a parent index is out of range or equals its node");
+    if (e & 1u) return fail(c, BIC_ERR_TABLE_TOO_LARGE, "a family's count table q*r exceeds 2^28 cells");
+    if (e & 4u) return fail(c, BIC_ERR_ARG, "counts_off does not match q*r of a family");
+    return BIC_OK;
+}
+
+// keys of T instances sit in c->keybuf: look them up, insert + count the unseen families.
+int resolve_instances(bic_ctx *c, long long T, int n_per_dag) {
+    TRY(cache_ensure(c, T));
+    CU(c->inst.ensure((size_t)T * sizeof(int)));
+    CU(c->flag.ensure((size_t)T * sizeof(u32)));
+    CU(c->rank.ensure((size_t)T * sizeof(u32)));
+    CU(c->cells_arr.ensure((size_t)T * sizeof(u32)));
+    CU(c->class_jobs.ensure((size_t)T * NCLASS * sizeof(int)));
+    unsigned g = nblk(T, 256);
+    k_probe<<<g, 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->Wk, T, n_per_dag, c->dag_bad.as<uint8_t>(), c->table,
+                                      (u32)(c->table_cap - 1), c->regkeys, c->inst.as<int>()); LAUNCH(c);
+    k_owner_flags<<<g, 256, 0, c->stream>>>(c->inst.as<int>(), c->table, T, c->flag.as<u32>()); LAUNCH(c);
+    TRY((scan_excl<u32, u32>(c, c->flag.as<u32>(), T, c->rank.as<u32>(), &c->d_hdr->f_new, c->bsum32)));
+    k_finalize<<<g, 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->W64, T, c->inst.as<int>(), c->flag.as<u32>(),
+                                         c->rank.as<u32>(), c->reg_count, c->regkeys, c->table, c->d_card, c->N,
+                                         (u32)T, c->d_hdr, c->cells_arr.as<u32>(), c->class_jobs.as<int>()); LAUNCH(c);
+    CU(cudaGetLastError());
+    TRY(header_fetch(c));
+    long long f_new = c->h_hdr->f_new;
+    c->lookups += T;
+    c->misses += f_new;
+    int rc = check_header_err(c);
+    if (rc != BIC_OK) {   // new ids were published without scores: drop the whole cache
+        cache_clear(c);
+        return rc;
+    }
+    if (f_new) {
+        rc = run_count(c, c->regkeys, c->reg_count, f_new, T, c->reg_ll, c->reg_np, false);
+        if (rc != BIC_OK) { cache_clear(c); return rc; }
+        c->reg_count += f_new;
+    }
+    return BIC_OK;
+}
+
+// Resolve the CUDA-event pairs recorded around the count launches of this call.
+int finish_call(bic_ctx *c) {
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &p : c->ev_used) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->prof.count_ms += ms;
+        c->ev_pool.push_back(p);
+    }
+    c->ev_used.clear();
+    return BIC_OK;
+}
+
+// Host or device input -> device pointer (staged when host).
+template <typename T>
+int stage_in(bic_ctx *c, const T *src, size_t count, int flags, DevBuf &buf, const T **out) {
+    if (flags & BIC_FLAG_DEVICE_PTRS) { *out = src; return BIC_OK; }
+    CU(buf.ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *out = buf.as<T>();
+    return BIC_OK;
+}
+
+int begin_call(bic_ctx *c, int metric, bool need_metric) {
+    if (!c->data) return fail(c, BIC_ERR_NO_DATASET, "no dataset: call bic_set_dataset first");
+    if (need_metric && (metric < BIC_METRIC_BIC || metric > BIC_METRIC_AIC)) return fail(c, BIC_ERR_ARG, "unknown metric");
+    CU(cudaSetDevice(c->device));
+    TRY(refresh_ntotal(c));
+    return BIC_OK;
+}
+
+long long sub_batch_dags(bic_ctx *c) {
+    const long long max_inst = 1ll << 22;
+    return std::max<long long>(1, max_inst / c->n);
+}
+
+enum DagFormat { FMT_ADJ, FMT_CSR, FMT_WIRE };
+
+int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_t B, int metric, double *out,
+               int64_t *n_invalid, int flags) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    TRY(begin_call(c, metric, true));
+    if (B < 0 || (B > 0 && (!p0 || !out))) return fail(c, BIC_ERR_ARG, "null pointer or negative batch size");
+    if (fmt == FMT_WIRE && c->n > 32) return fail(c, BIC_ERR_ARG, "wire format supports n <= 32");
+    if (flags & BIC_FLAG_NO_CACHE) TRY(cache_clear(c));
+    const int n = c->n;
+    const double pen = metric_penalty(c, metric);
+    const bool dev = (flags & BIC_FLAG_DEVICE_PTRS) != 0;
+    long long invalid = 0;
+    const long long Bs = sub_batch_dags(c);
+    std::vector<long long> h_off;   // CSR offsets are needed on the host to slice a host batch
+    for (long long b0 = 0; b0 < B; b0 += Bs) {
+        long long Bc = std::min<long long>(Bs, B - b0);
+        long long T = Bc * n;
+        CU(c->keybuf.ensure((size_t)T * c->Wk * sizeof(u64)));
+        CU(c->dag_bad.ensure((size_t)Bc));
+        CU(cudaMemsetAsync(c->dag_bad.p, 0, (size_t)Bc, c->stream));
+        TRY(header_reset(c));
+        if (fmt == FMT_ADJ) {
+            const uint8_t *adj = nullptr;
+            TRY(stage_in(c, (const uint8_t *)p0 + b0 * (long long)n * n, (size_t)Bc * n * n, flags, c->in_stage, &adj));
+            k_keys_adj<<<nblk(T, 256), 256, 0, c->stream>>>(adj, Bc, n, c->W64, c->keybuf.as<u64>(), c->dag_bad.as<uint8_t>()); LAUNCH(c);
+        } else if (fmt == FMT_CSR) {
+            const long long *off = (const long long *)p0 + b0 * n;
+            const int *par = (const int *)p1;
+            const long long *d_off = nullptr;
+            const int *d_par = nullptr;
+            if (dev) {
+                d_off = off;     // absolute offsets into the caller's device array
+                d_par = par;
+            } else {
+                long long e0 = off[0], e1 = off[T];
+                if (e1 < e0) return fail(c, BIC_ERR_ARG, "CSR offsets are not monotone");
+                h_off.resize((size_t)T + 1);
+                for (long long i = 0; i <= T; ++i) h_off[(size_t)i] = off[i] - e0;
+                TRY(stage_in(c, h_off.data(), (size_t)T + 1, 0, c->in_stage, &d_off));
+                TRY(stage_in(c, par + e0, (size_t)(e1 - e0), 0, c->in_stage2, &d_par));
+                CU(cudaStreamSynchronize(c->stream));   // h_off is reused by the next sub-batch
+            }
+            k_keys_csr<<<nblk(T, 256), 256, 0, c->stream>>>(d_off, d_par, nullptr, T, n, c->W64, c->keybuf.as<u64>(),
+                                                            c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
+        } else {
+            const uint8_t *lab = nullptr;
+            const u32 *eb = nullptr;
+            TRY(stage_in(c, (const uint8_t *)p0 + b0 * n, (size_t)Bc * n, flags, c->in_stage, &lab));
+            TRY(stage_in(c, (const u32 *)p1 + b0 * n, (size_t)Bc * n, flags, c->in_stage2, &eb));
+            k_keys_wire<<<nblk(Bc, 128), 128, 0, c->stream>>>(lab, eb, Bc, n, c->keybuf.as<u64>(), c->dag_bad.as<uint8_t>()); LAUNCH(c);
+        }
+        if ((flags & BIC_FLAG_NO_CYCLE_CHECK) || fmt == FMT_WIRE) {
+            k_count_bad<<<nblk(Bc, 256), 256, 0, c->stream>>>(c->dag_bad.as<uint8_t>(), Bc, c->d_hdr); LAUNCH(c);
+        } else {
+            k_acyclic<<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
+                                                                             c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
+        }
+        CU(cudaGetLastError());
+        TRY(resolve_instances(c, T, n));
+        invalid += c->h_hdr->n_invalid;
+        double *d_out = out + b0;
+        if (!dev) {
+            CU(c->out_stage.ensure((size_t)Bc * sizeof(double)));
+            d_out = c->out_stage.as<double>();
+        }
+        k_gather_dags<<<nblk(Bc, 128), 128, 0, c->stream>>>(c->inst.as<int>(), c->table, Bc, n, c->dag_bad.as<uint8_t>(),
+                                                            c->reg_ll, c->reg_np, pen, d_out); LAUNCH(c);
+        CU(cudaGetLastError());
+        if (!dev) CU(cudaMemcpyAsync(out + b0, d_out, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TRY(finish_call(c));
+    }
+    if (n_invalid) *n_invalid = invalid;
+    return BIC_OK;
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" {
+
+int bic_version(void) { return BICGPU_VERSION; }
+
+const char *bic_last_error(const bic_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int bic_create(bic_ctx **out, int device) {
+    bic_ctx *c = nullptr;
+    if (!out) return fail(c, BIC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(c, BIC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libbicgpu has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(c, BIC_ERR_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    CU(cudaSetDevice(device));
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(c, BIC_ERR_CUDA, std::string("libbicgpu is built for sm_100a only; device is ") + prop.name);
+    bic_ctx *ctx = new bic_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    c = ctx;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_hdr, sizeof(Header)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_hdr, sizeof(Header)) != cudaSuccess) {
+        g_create_error = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return BIC_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return BIC_OK;
+}
+
+int bic_destroy(bic_ctx *c) {
+    if (!c) return BIC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cache_free(c);
+    DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
+                      &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
+                      &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll};
+    for (DevBuf *b : bufs) b->release();
+    if (c->data) cudaFree(c->data);
+    if (c->d_card) cudaFree(c->d_card);
+    if (c->d_hdr) cudaFree(c->d_hdr);
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    for (auto &p : c->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return BIC_OK;
+}
+
+int bic_set_stream(bic_ctx *c, void *cuda_stream) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return BIC_OK;
+}
+
+int bic_sync(bic_ctx *c) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return BIC_OK;
+}
+
+int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int64_t stride, const int32_t *card,
+                    int is_device) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!codes || !card) return fail(c, BIC_ERR_ARG, "codes/card is NULL");
+    if (n < 1 || n > NMAX) return fail(c, BIC_ERR_ARG, "n must be in 1..1024");
+    if (N < 1 || N >= (1ll << 31)) return fail(c, BIC_ERR_ARG, "N must be in 1..2^31-1 (int32 count tables)");
+    if (stride < N) return fail(c, BIC_ERR_ARG, "stride < N");
+    for (int v = 0; v < n; ++v)
+        if (card[v] < 1 || card[v] > 255) return fail(c, BIC_ERR_ARG, "cardinalities must be in 1..255");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    // the key width depends on n: drop the old cache entirely
+    cache_free(c);
+    c->lookups = c->misses = 0;
+    if (c->data) { cudaFree(c->data); c->data = nullptr; }
+    if (c->d_card) { cudaFree(c->d_card); c->d_card = nullptr; }
+    long long pstride = (N + 127) / 128 * 128;   // every column 128-byte aligned; tail rows hold state 0
+    CU(cudaMalloc(&c->data, (size_t)pstride * n));
+    CU(cudaMalloc(&c->d_card, (size_t)n * sizeof(int)));
+    CU(cudaMemsetAsync(c->data, 0, (size_t)pstride * n, c->stream));
+    CU(cudaMemcpy2DAsync(c->data, (size_t)pstride, codes, (size_t)stride, (size_t)N, (size_t)n,
+                         is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_card, card, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->N = N; c->n = n; c->stride = pstride; c->W64 = (n + 63) / 64; c->Wk = c->W64 + 1;
+    c->card.assign(card, card + n);
+    c->ntotal_dirty = true;
+    // validate codes < card on the device
+    TRY(header_reset(c));
+    dim3 grid((unsigned)std::min<long long>(1024, (N + 255) / 256), (unsigned)n);
+    k_validate<<<grid, 256, 0, c->stream>>>(c->data, N, pstride, n, c->d_card, &c->d_hdr->err); LAUNCH(c);
+    CU(cudaGetLastError());
+    TRY(header_fetch(c));
+    if (c->h_hdr->err) {
+        cudaFree(c->data);
+        c->data = nullptr;
+        return fail(c, BIC_ERR_BAD_CODE, "dataset holds a state code >= its declared cardinality");
+    }
+    return BIC_OK;
+}
+
+int bic_count_families(bic_ctx *c, const int32_t *node, const int64_t *parent_off, const int32_t *parents, int64_t F,
+                       const int64_t *counts_off, int32_t *counts_out, int flags) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    TRY(begin_call(c, 0, false));
+    if (F < 0 || (F > 0 && (!node || !parent_off || !counts_off || !counts_out))) return fail(c, BIC_ERR_ARG, "null pointer or negative F");
+    if (F == 0) return BIC_OK;
+    if (F > (1ll << 22)) return fail(c, BIC_ERR_ARG, "bic_count_families: at most 2^22 families per call");
+    const bool dev = (flags & BIC_FLAG_DEVICE_PTRS) != 0;
+    long long E = 0, cells_total = 0;
+    if (!dev) { E = parent_off[F]; cells_total = counts_off[F]; }
+    else {
+        CU(cudaMemcpyAsync(&E, parent_off + F, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&cells_total, counts_off + F, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const int *d_node = nullptr, *d_par = nullptr;
+    const long long *d_off = nullptr, *d_coff = nullptr;
+    TRY(stage_in(c, (const int *)node, (size_t)F, flags, c->in_stage, &d_node));
+    TRY(stage_in(c, (const long long *)parent_off, (size_t)F + 1, flags, c->in_stage2, &d_off));
+    TRY(stage_in(c, (const int *)parents, (size_t)std::max<long long>(E, 0), flags, c->in_stage3, &d_par));
+    TRY(stage_in(c, (const long long *)counts_off, (size_t)F + 1, flags, c->in_stage4, &d_coff));
+    CU(c->keybuf.ensure((size_t)F * c->Wk * sizeof(u64)));
+    CU(c->cells_arr.ensure((size_t)F * sizeof(u32)));
+    CU(c->class_jobs.ensure((size_t)F * NCLASS * sizeof(int)));
+    CU(c->tmp_ll.ensure((size_t)F * 2 * sizeof(double)));
+    TRY(header_reset(c));
+    k_keys_csr<<<nblk(F, 256), 256, 0, c->stream>>>(d_off, d_par, d_node, F, c->n, c->W64, c->keybuf.as<u64>(), nullptr, c->d_hdr); LAUNCH(c);
+    k_describe_direct<<<nblk(F, 256), 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->W64, F, c->d_card, c->N, (u32)F, c->d_hdr,
+                                                           c->cells_arr.as<u32>(), c->class_jobs.as<int>()); LAUNCH(c);
+    CU(cudaGetLastError());
+    TRY(header_fetch(c));
+    TRY(check_header_err(c));
+    TRY(run_count(c, c->keybuf.as<u64>(), 0, F, F, c->tmp_ll.as<double>(), c->tmp_ll.as<double>() + F, true));
+    int *d_out = counts_out;
+    if (!dev) {
+        CU(c->out_stage.ensure((size_t)std::max<long long>(cells_total, 1) * sizeof(int)));
+        d_out = c->out_stage.as<int>();
+    }
+    k_copy_tables<<<(unsigned)F, 256, 0, c->stream>>>(c->arena.as<u32>(), c->table_off.as<u64>(), c->cells_arr.as<u32>(), d_coff, d_out, c->d_hdr); LAUNCH(c);
+    CU(cudaGetLastError());
+    TRY(header_fetch(c));
+    TRY(check_header_err(c));
+    if (!dev && cells_total) CU(cudaMemcpyAsync(counts_out, d_out, (size_t)cells_total * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return finish_call(c);
+}
+
+int bic_score_families(bic_ctx *c, const int32_t *node, const int64_t *parent_off, const int32_t *parents, int64_t F,
+                       int metric, double *out, int flags) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    TRY(begin_call(c, metric, true));
+    if (F < 0 || (F > 0 && (!node || !parent_off || !out))) return fail(c, BIC_ERR_ARG, "null pointer or negative F");
+    if (flags & BIC_FLAG_NO_CACHE) TRY(cache_clear(c));
+    const bool dev = (flags & BIC_FLAG_DEVICE_PTRS) != 0;
+    const double pen = metric_penalty(c, metric);
+    const long long Fs = 1ll << 22;
+    std::vector<long long> h_off;
+    for (long long f0 = 0; f0 < F; f0 += Fs) {
+        long long Fc = std::min<long long>(Fs, F - f0);
+        const int *d_node = nullptr, *d_par = nullptr;
+        const long long *d_off = nullptr;
+        if (dev) {
+            d_node = (const int *)node + f0; d_off = (const long long *)parent_off + f0; d_par = (const int *)parents;
+        } else {
+            const long long *off = (const long long *)parent_off + f0;
+            long long e0 = off[0], e1 = off[Fc];
+            if (e1 < e0) return fail(c, BIC_ERR_ARG, "parent_off is not monotone");
+            h_off.resize((size_t)Fc + 1);
+            for (long long i = 0; i <= Fc; ++i) h_off[(size_t)i] = off[i] - e0;
+            TRY(stage_in(c, (const int *)node + f0, (size_t)Fc, 0, c->in_stage, &d_node));
+            TRY(stage_in(c, h_off.data(), (size_t)Fc + 1, 0, c->in_stage2, &d_off));
+            TRY(stage_in(c, (const int *)parents + e0, (size_t)(e1 - e0), 0, c->in_stage3, &d_par));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        CU(c->keybuf.ensure((size_t)Fc * c->Wk * sizeof(u64)));
+        TRY(header_reset(c));
+        k_keys_csr<<<nblk(Fc, 256), 256, 0, c->stream>>>(d_off, d_par, d_node, Fc, c->n, c->W64, c->keybuf.as<u64>(), nullptr, c->d_hdr); LAUNCH(c);
+        CU(cudaGetLastError());
+        TRY(resolve_instances(c, Fc, 0));
+        double *d_out = out + f0;
+        if (!dev) {
+            CU(c->out_stage.ensure((size_t)Fc * sizeof(double)));
+            d_out = c->out_stage.as<double>();
+        }
+        k_gather_fams<<<nblk(Fc, 256), 256, 0, c->stream>>>(c->inst.as<int>(), c->table, Fc, c->reg_ll, c->reg_np, pen, d_out); LAUNCH(c);
+        CU(cudaGetLastError());
+        if (!dev) CU(cudaMemcpyAsync(out + f0, d_out, (size_t)Fc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TRY(finish_call(c));
+    }
+    return BIC_OK;
+}
+
+int bic_score_dags_adj(bic_ctx *c, const uint8_t *adj, int64_t B, int metric, double *out, int64_t *n_invalid, int flags) {
+    return score_dags(c, FMT_ADJ, adj, nullptr, B, metric, out, n_invalid, flags);
+}
+
+int bic_score_dags_csr(bic_ctx *c, const int64_t *off, const int32_t *parents, int64_t B, int metric, double *out,
+                       int64_t *n_invalid, int flags) {
+    return score_dags(c, FMT_CSR, off, parents, B, metric, out, n_invalid, flags);
+}
+
+int bic_score_dags_wire(bic_ctx *c, const uint8_t *labels, const uint32_t *ebits, int64_t B, int metric, double *out,
+                        int64_t *n_invalid, int flags) {
+    if (c && B > 0 && !ebits) return fail(c, BIC_ERR_ARG, "ebits is NULL");
+    return score_dags(c, FMT_WIRE, labels, ebits, B, metric, out, n_invalid, flags);
+}
+
+int bic_cache_clear(bic_ctx *c) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return cache_clear(c);
+}
+
+int bic_cache_reserve(bic_ctx *c, int64_t families) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->data) return fail(c, BIC_ERR_NO_DATASET, "no dataset: call bic_set_dataset first");
+    CU(cudaSetDevice(c->device));
+    long long extra = families - c->reg_count;
+    return extra > 0 ? cache_ensure(c, extra) : BIC_OK;
+}
+
+int bic_cache_stats(bic_ctx *c, bic_cache_stats_t *out) {
+    if (!c || !out) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    out->families = c->reg_count;
+    out->capacity = c->reg_cap;
+    out->lookups = c->lookups;
+    out->misses = c->misses;
+    out->bytes = (int64_t)(c->table_cap * sizeof(u32) + (size_t)c->reg_cap * (c->Wk * sizeof(u64) + 2 * sizeof(double)));
+    return BIC_OK;
+}
+
+int bic_profile_enable(bic_ctx *c, int on) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->prof_on = on != 0;
+    return BIC_OK;
+}
+
+int bic_profile_reset(bic_ctx *c) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->prof = bic_profile_t{};
+    return BIC_OK;
+}
+
+int bic_profile_get(bic_ctx *c, bic_profile_t *out) {
+    if (!c || !out) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = c->prof;
+    return BIC_OK;
+}
+
+int bic_comm_unique_id(uint8_t id_out[128]) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (!id_out) return BIC_ERR_ARG;
+    if (!g_nccl.load()) { g_create_error = g_nccl.err; return BIC_ERR_NCCL; }
+    nccl_uid id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) { g_create_error = "ncclGetUniqueId failed"; return BIC_ERR_NCCL; }
+    memcpy(id_out, id.internal, 128);
+    return BIC_OK;
+}
+
+int bic_comm_init(bic_ctx *c, const uint8_t id[128], int rank, int world) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(c, BIC_ERR_ARG, "bad rank/world/id");
+    {
+        std::lock_guard<std::mutex> lk2(g_nccl_mu);
+        if (!g_nccl.load()) return fail(c, BIC_ERR_NCCL, g_nccl.err);
+    }
+    CU(cudaSetDevice(c->device));
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    nccl_uid uid;
+    memcpy(uid.internal, id, 128);
+    int rc = g_nccl.CommInitRank(&c->comm, world, uid, rank);
+    if (rc != 0) {
+        c->comm = nullptr;
+        return fail(c, BIC_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    }
+    c->rank_id = rank;
+    c->world = world;
+    c->ntotal_dirty = true;
+    TRY(cache_clear(c));   // cached terms were computed on this rank's rows only
+    return BIC_OK;
+}
+
+int bic_comm_destroy(bic_ctx *c) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    c->world = 1; c->rank_id = 0;
+    c->ntotal_dirty = true;
+    TRY(cache_clear(c));
+    return BIC_OK;
+}
+
+}  // extern "C"

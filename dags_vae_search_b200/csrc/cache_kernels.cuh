@@ -1,0 +1,393 @@
+// k5 (candidate -> family keys), acyclicity check, k4 (family-score cache: dedup / lookup /
+// insert / gather-sum) and the small device scans that make family ids deterministic.
+//
+// Reference behaviour replaced: bnlearn.py:38-44 (relabel + adjacency serialisation),
+// bnlearn_score.R:7-13,35 (parse adjacency, amat<- rejects cycles).  The cache itself has no
+// reference equivalent (the reference recounts every family of every DAG).
+#pragma once
+#include "common.cuh"
+
+namespace bic {
+
+// ------------------------------------------------------------------------------- keys
+// adj [B][n][n] uint8, row = parent, col = child.  One thread per (b, child i); consecutive
+// threads read consecutive bytes of the same adjacency row.
+__global__ void k_keys_adj(const uint8_t *__restrict__ adj, long long B, int n, int W64, u64 *keybuf,
+                           uint8_t *dag_bad) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n) return;
+    long long b = t / n;
+    int i = (int)(t - b * n);
+    const uint8_t *a = adj + b * (long long)n * n;
+    u64 *key = keybuf + t * (W64 + 1);
+    key[0] = (u64)i;
+    for (int w = 0; w < W64; ++w) {
+        u64 m = 0;
+        int p1 = min(n, w * 64 + 64);
+        for (int p = w * 64; p < p1; ++p)
+            if (a[(long long)p * n + i]) m |= 1ull << (p & 63);
+        key[1 + w] = m;
+    }
+    if (a[(long long)i * n + i]) dag_bad[b] = 1;  // self loop
+}
+
+// Parent lists in CSR.  node == nullptr: instance t is family (t / n, t % n) of a DAG batch.
+__global__ void k_keys_csr(const long long *__restrict__ off, const int *__restrict__ parents,
+                           const int *__restrict__ node, long long T, int n, int W64, u64 *keybuf,
+                           uint8_t *dag_bad, Header *hdr) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    int i = node ? node[t] : (int)(t % n);
+    u64 *key = keybuf + t * (W64 + 1);
+    for (int w = 0; w < W64; ++w) key[1 + w] = 0;
+    bool bad = (i < 0 || i >= n);
+    key[0] = bad ? 0 : (u64)i;
+    long long e0 = off[t], e1 = off[t + 1];
+    for (long long e = e0; e < e1; ++e) {
+        int p = parents[e];
+        if (p < 0 || p >= n || p == i) { bad = true; continue; }
+        key[1 + (p >> 6)] |= 1ull << (p & 63);
+    }
+    if (bad) {
+        if (node) atomicOr(&hdr->err, 2u);   // family API: hard error
+        else dag_bad[t / n] = 1;             // DAG API: reject this DAG
+    }
+}
+
+// Reference wire format (src/toolkit/labeled.py:132-154): vertex v carries label l_v (= BN
+// variable), bit u of ebits[v] <=> edge vertex u -> vertex v, u < v.  bnlearn.py:38-42 relabels
+// vertices to variables; here one thread per DAG does that and writes the n keys in variable
+// order.  n <= 32, so one mask word.
+__global__ void k_keys_wire(const uint8_t *__restrict__ labels, const u32 *__restrict__ ebits,
+                            long long B, int n, u64 *keybuf, uint8_t *dag_bad) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint8_t *lab = labels + b * n;
+    const u32 *eb = ebits + b * n;
+    u32 seen = 0;
+    for (int v = 0; v < n; ++v) {
+        int l = lab[v];
+        if (l < n) seen |= 1u << l;
+    }
+    u32 full = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
+    if (seen != full) {  // bnlearn.py:35 asserts the labels are exactly 0..n-1
+        dag_bad[b] = 1;
+        for (int v = 0; v < n; ++v) { keybuf[(b * n + v) * 2] = (u64)v; keybuf[(b * n + v) * 2 + 1] = 0; }
+        return;
+    }
+    for (int v = 0; v < n; ++v) {
+        u32 e = eb[v] & ((v == 0) ? 0u : ((v >= 32) ? 0xffffffffu : ((1u << v) - 1u)));
+        u64 m = 0;
+        while (e) {
+            int u = __ffs(e) - 1;
+            e &= e - 1;
+            m |= 1ull << lab[u];
+        }
+        long long t = b * n + lab[v];
+        keybuf[t * 2] = (u64)lab[v];
+        keybuf[t * 2 + 1] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------- acyclic
+// One warp per DAG: peel parentless vertices (Kahn) on bitmasks held in shared memory.
+// dag_bad[b] in: self loop / bad index; out: also set when a cycle remains.
+constexpr int ACYC_WARPS = 4;
+__global__ void __launch_bounds__(ACYC_WARPS * 32)
+k_acyclic(const u64 *__restrict__ keybuf, long long B, int n, int W64, uint8_t *dag_bad, Header *hdr) {
+    __shared__ u64 s_alive[ACYC_WARPS][W64MAX];
+    __shared__ u64 s_next[ACYC_WARPS][W64MAX];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long b = (long long)blockIdx.x * ACYC_WARPS + warp;
+    if (b >= B) return;
+    int Wk = W64 + 1;
+    u64 *alive = s_alive[warp], *next = s_next[warp];
+    bool bad = dag_bad[b] != 0;
+    if (!bad) {
+        for (int w = lane; w < W64; w += 32) {
+            int bits = min(64, n - w * 64);
+            u64 m = (bits >= 64) ? ~0ull : ((1ull << bits) - 1ull);
+            alive[w] = m;
+            next[w] = m;
+        }
+        __syncwarp();
+        const u64 *keys = keybuf + b * (long long)n * Wk;
+        while (true) {
+            for (int i = lane; i < n; i += 32) {
+                if (!((alive[i >> 6] >> (i & 63)) & 1ull)) continue;
+                const u64 *pm = keys + (long long)i * Wk + 1;
+                bool blocked = false;
+                for (int w = 0; w < W64; ++w) blocked = blocked || ((pm[w] & alive[w]) != 0);
+                if (!blocked) atomicAnd(&next[i >> 6], ~(1ull << (i & 63)));
+            }
+            __syncwarp();
+            bool changed = false, any = false;
+            for (int w = 0; w < W64; ++w) {   // every lane reads the same words: uniform result
+                changed = changed || (next[w] != alive[w]);
+                any = any || (next[w] != 0);
+            }
+            __syncwarp();
+            for (int w = lane; w < W64; w += 32) alive[w] = next[w];
+            __syncwarp();
+            if (!any) break;
+            if (!changed) { bad = true; break; }
+        }
+    }
+    if (lane == 0 && bad) {
+        dag_bad[b] = 1;
+        atomicAdd(&hdr->n_invalid, 1u);
+    }
+}
+
+// Without the cycle check the rejected DAGs (self loop, bad index) still have to be counted.
+__global__ void k_count_bad(const uint8_t *dag_bad, long long B, Header *hdr) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && dag_bad[b]) atomicAdd(&hdr->n_invalid, 1u);
+}
+
+// ------------------------------------------------------------------------ cache: probe
+// inst[t] >= 0: family id (cache hit);  -1: instance of a rejected DAG;  <= -2: slot -2-inst
+// holds a PENDING entry of this batch.  The PENDING entry keeps the *smallest* instance index
+// among duplicates, so the owner — and with it every family id — does not depend on thread
+// timing (row-sharded ranks must agree on ids and table offsets).
+__global__ void k_probe(const u64 *__restrict__ keybuf, int Wk, long long T, int n_per_dag,
+                        const uint8_t *__restrict__ dag_bad, u32 *table, u32 mask,
+                        const u64 *__restrict__ regkeys, int *inst) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    if (n_per_dag && dag_bad[t / n_per_dag]) { inst[t] = -1; return; }
+    const u64 *key = keybuf + t * Wk;
+    u32 s = (u32)hash_key(key, Wk) & mask;
+    const u32 mine = ENT_PENDING | (u32)t;
+    while (true) {
+        u32 e = *((volatile u32 *)(table + s));
+        if (e == ENT_EMPTY) {
+            u32 old = atomicCAS(table + s, ENT_EMPTY, mine);
+            if (old == ENT_EMPTY) { inst[t] = -2 - (int)s; return; }
+            e = old;
+        }
+        if (e & ENT_PENDING) {
+            long long t2 = (long long)(e & ~ENT_PENDING);
+            if (keys_equal(key, keybuf + t2 * Wk, Wk)) {
+                atomicMin(table + s, mine);
+                inst[t] = -2 - (int)s;
+                return;
+            }
+        } else {
+            long long id = (long long)e - 1;
+            if (keys_equal(key, regkeys + id * Wk, Wk)) { inst[t] = (int)id; return; }
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void k_owner_flags(const int *__restrict__ inst, const u32 *__restrict__ table, long long T,
+                              u32 *flag) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    int v = inst[t];
+    flag[t] = (v <= -2 && table[-2 - v] == (ENT_PENDING | (u32)t)) ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------------------- scan
+// Exclusive scan, three launches; thread t of a block owns ITEMS consecutive elements.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(const TI *__restrict__ in, long long n, TO *bsum) {
+    __shared__ TO sh[SCAN_THREADS / 32];
+    long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_ITEMS;
+    TO s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) s += (TO)in[base + i];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TO tot = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) tot += sh[w];
+        bsum[blockIdx.x] = tot;
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(1024) k_scan_bsums(TO *bsum, int nb, TO *total) {
+    __shared__ TO sh[1024];
+    __shared__ TO carry;
+    int tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        int i = base + tid;
+        TO v = (i < nb) ? bsum[i] : (TO)0;
+        sh[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            TO x = (tid >= o) ? sh[tid - o] : (TO)0;
+            __syncthreads();
+            sh[tid] += x;
+            __syncthreads();
+        }
+        TO incl = sh[tid], c = carry;
+        __syncthreads();
+        if (i < nb) bsum[i] = c + incl - v;
+        if (tid == 1023) carry = c + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *total = carry;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TI *__restrict__ in, long long n,
+                                                             const TO *__restrict__ bsum, TO *out) {
+    __shared__ TO sh[SCAN_THREADS];
+    long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_ITEMS;
+    TO loc[SCAN_ITEMS];
+    TO s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        loc[i] = (base + i < n) ? (TO)in[base + i] : (TO)0;
+        s += loc[i];
+    }
+    int tid = threadIdx.x;
+    sh[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+        TO x = (tid >= o) ? sh[tid - o] : (TO)0;
+        __syncthreads();
+        sh[tid] += x;
+        __syncthreads();
+    }
+    TO run = bsum[blockIdx.x] + sh[tid] - s;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += loc[i];
+    }
+}
+
+// --------------------------------------------------------------- describe a new family
+// Decodes a key into the count-kernel class, appends the job to its class list and adds the
+// family's algorithmic bytes to the header.  Families whose table would exceed MAX_CELLS set
+// err bit 0 and get no job.
+__device__ __forceinline__ void describe_family(const u64 *key, int W64, const int *__restrict__ card,
+                                                long long N, u32 j, u32 max_jobs, Header *hdr,
+                                                u32 *cells_arr, int *class_jobs) {
+    int node = (int)key[0];
+    u64 r = (u64)card[node];
+    u64 q = 1;
+    int k = 0;
+    bool over = false;
+    for (int w = 0; w < W64; ++w) {
+        u64 m = key[1 + w];
+        while (m) {
+            int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            u64 c = (u64)card[w * 64 + b];
+            if (c > 1) {
+                ++k;
+                q *= c;
+                if (q > MAX_CELLS) { over = true; q = MAX_CELLS + 1; }
+            }
+        }
+    }
+    u64 cells = q * r;
+    if (over || cells > MAX_CELLS) {
+        atomicOr(&hdr->err, 1u);
+        cells_arr[j] = 0;
+        return;
+    }
+    cells_arr[j] = (u32)cells;
+    int cls = cells <= CLASS0_CELLS ? 0 : cells <= CLASS1_CELLS ? 1 : cells <= CLASS2_CELLS ? 2 : 3;
+    u32 pos = atomicAdd(&hdr->class_count[cls], 1u);
+    class_jobs[(long long)cls * max_jobs + pos] = (int)j;
+    atomicAdd(&hdr->alg_bytes, (u64)(k + 1) * (u64)N + 4ull * cells);
+}
+
+// Owners of PENDING entries take id = base + rank, publish their key in the registry and
+// finalise the table entry; then describe the new family as job `rank`.
+__global__ void k_finalize(const u64 *__restrict__ keybuf, int W64, long long T, int *inst,
+                           const u32 *__restrict__ flag, const u32 *__restrict__ rank, long long base,
+                           u64 *regkeys, u32 *table, const int *__restrict__ card, long long N,
+                           u32 max_jobs, Header *hdr, u32 *cells_arr, int *class_jobs) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T || !flag[t]) return;
+    int Wk = W64 + 1;
+    u32 j = rank[t];
+    long long id = base + j;
+    const u64 *key = keybuf + t * Wk;
+    for (int w = 0; w < Wk; ++w) regkeys[id * Wk + w] = key[w];
+    table[-2 - inst[t]] = (u32)(id + 1);
+    inst[t] = (int)id;
+    describe_family(key, W64, card, N, j, max_jobs, hdr, cells_arr, class_jobs);
+}
+
+// Cache-bypassing path (bic_count_families): every listed family is job t.
+__global__ void k_describe_direct(const u64 *__restrict__ keybuf, int W64, long long T,
+                                  const int *__restrict__ card, long long N, u32 max_jobs, Header *hdr,
+                                  u32 *cells_arr, int *class_jobs) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    describe_family(keybuf + t * (W64 + 1), W64, card, N, (u32)t, max_jobs, hdr, cells_arr, class_jobs);
+}
+
+// Which jobs need their table in HBM: S > 1 slices, class 3, or the caller wants the counts.
+struct NeedArgs { int S[NCLASS]; int all; };
+__global__ void k_table_need(const u32 *__restrict__ cells_arr, u32 njobs, NeedArgs a, u32 *need) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    u32 cells = cells_arr[j];
+    int cls = cells <= CLASS0_CELLS ? 0 : cells <= CLASS1_CELLS ? 1 : cells <= CLASS2_CELLS ? 2 : 3;
+    need[j] = (a.all || cls == 3 || a.S[cls] > 1) ? cells : 0u;
+}
+
+// -------------------------------------------------------------------- rehash on growth
+__global__ void k_rehash(const u64 *__restrict__ regkeys, int Wk, long long count, u32 *table, u32 mask) {
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    u32 s = (u32)hash_key(regkeys + id * Wk, Wk) & mask;
+    while (atomicCAS(table + s, ENT_EMPTY, (u32)(id + 1)) != ENT_EMPTY) s = (s + 1) & mask;
+}
+
+// ------------------------------------------------------------------------------ gather
+__device__ __forceinline__ long long resolve_id(int v, const u32 *__restrict__ table) {
+    return v >= 0 ? (long long)v : (long long)table[-2 - v] - 1;
+}
+
+// Per-DAG sum of its n family terms, in variable order (matches the oracle's summation order).
+__global__ void k_gather_dags(const int *__restrict__ inst, const u32 *__restrict__ table, long long B, int n,
+                              const uint8_t *__restrict__ dag_bad, const double *__restrict__ ll,
+                              const double *__restrict__ np, double pen, double *out) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (dag_bad[b]) { out[b] = __longlong_as_double(0x7ff8000000000000LL); return; }
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        long long id = resolve_id(inst[b * n + i], table);
+        s += ll[id] - pen * np[id];
+    }
+    out[b] = s;
+}
+
+__global__ void k_gather_fams(const int *__restrict__ inst, const u32 *__restrict__ table, long long T,
+                              const double *__restrict__ ll, const double *__restrict__ np, double pen,
+                              double *out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    long long id = resolve_id(inst[t], table);
+    out[t] = ll[id] - pen * np[id];
+}
+
+// ------------------------------------------------------------------- dataset validation
+__global__ void k_validate(const uint8_t *__restrict__ data, long long N, long long stride, int n,
+                           const int *__restrict__ card, u32 *bad) {
+    int v = blockIdx.y;
+    int c = card[v];
+    const uint8_t *col = data + (long long)v * stride;
+    bool b = false;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x)
+        b = b || (col[r] >= c);
+    if (b) atomicOr(bad, 1u);
+}
+
+}  // namespace bic

@@ -1,0 +1,65 @@
+// Shared definitions for libbicgpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bic {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int KMAX = 32;                   // parents with cardinality > 1 in one family (2^28 cells cap => <= 27)
+constexpr int NMAX = 1024;                 // variables per dataset
+constexpr int W64MAX = NMAX / 64;          // bitmask words per parent set
+constexpr u32 ENT_EMPTY = 0u;              // hash-table entry: empty
+constexpr u32 ENT_PENDING = 0x80000000u;   // entry = PENDING | instance index while a batch is being deduplicated
+constexpr u64 MAX_CELLS = 1ull << 28;      // q*r limit of one count table (1 GiB of int32)
+
+// Count-kernel classes by table size (cells = q*r).  Classes 0..2 keep the table in shared
+// memory (one privatised histogram per CTA), class 3 counts straight into HBM with L2 atomics.
+constexpr int NCLASS = 4;
+constexpr u32 CLASS0_CELLS = 2048;         //   8 KB of int32 -> many CTAs per SM
+constexpr u32 CLASS1_CELLS = 12288;        //  48 KB
+constexpr u32 CLASS2_CELLS = 49152;        // 192 KB (one CTA per SM)
+
+// Device-written batch header, mirrored in pinned host memory once per sub-batch.
+struct Header {
+    u32 f_new;                 // families first seen in this sub-batch (exclusive-scan total)
+    u32 class_count[NCLASS];   // of those, per count-kernel class
+    u32 err;                   // bit 0: q*r over MAX_CELLS; bit 1: bad parent index
+    u32 n_invalid;             // DAGs rejected (cyclic, self loop, labels not a permutation)
+    u32 pad;
+    u64 alg_bytes;             // sum (k+1)*N + 4*q*r over the new families
+    u64 table_cells;           // cells of all count tables that must live in HBM (scan total)
+};
+
+__device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// Family key: word 0 = node, words 1..W64 = parent bitmask.
+__device__ __forceinline__ u64 hash_key(const u64 *key, int Wk) {
+    u64 h = 0x9E3779B97F4A7C15ULL;
+    for (int w = 0; w < Wk; ++w) h = mix64(h ^ key[w]) + 0x632BE59BD9B4E019ULL * (u64)(w + 1);
+    return h;
+}
+
+__device__ __forceinline__ bool keys_equal(const u64 *a, const u64 *b, int Wk) {
+    bool eq = true;
+    for (int w = 0; w < Wk; ++w) eq = eq && (a[w] == b[w]);
+    return eq;
+}
+
+// 128-bit streaming load of 16 consecutive rows of one state column (read once: keep out of L1).
+__device__ __forceinline__ uint4 ld_stream_v4(const uint8_t *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace bic

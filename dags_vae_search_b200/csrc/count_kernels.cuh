@@ -1,0 +1,269 @@
+// k2 (family count) + k3 (fused fp64 log-likelihood reduce).
+//
+// Replaces the arithmetic behind bnlearn::score(net, data, type = "bic") (call site
+// bnlearn_score.R:38): per family, mixed-radix parent configuration index per row,
+// contingency counts N_ijk, then sum N_ijk ln(N_ijk / N_ij).
+//
+// Work item = (family job, row slice).  A CTA streams its slice of the k+1 state columns with
+// 128-bit loads (16 rows per load), builds the cell index of each row in registers and counts
+// into a histogram that is private to the CTA: in shared memory for classes 0..2, straight in
+// HBM (L2 atomics) for class 3.  With one slice per family the fp64 reduce runs as the epilogue
+// on the shared-memory table; otherwise slices merge into the HBM table and the last slice to
+// finish (atomic ticket) reduces it.
+#pragma once
+#include "common.cuh"
+
+namespace bic {
+
+struct CountArgs {
+    const uint8_t *data;     // [n][stride] uint8 state codes
+    long long N;             // rows on this GPU
+    long long stride;
+    const int *card;
+    int W64;
+    const u64 *keys;         // family keys; job j uses keys + (key_base + j) * (W64 + 1)
+    long long key_base;
+    const int *jobs;         // job ids of this launch (one class)
+    int S;                   // row slices per family
+    u32 *arena;              // HBM count tables
+    const u32 *need;         // per job: cells if its table lives in HBM, else 0 (nullable)
+    const u64 *table_off;    // per job: offset into arena (valid where need != 0)
+    u32 *done;               // per job: slice tickets
+    double *ll_out;          // [key_base + j]
+    double *np_out;          // [key_base + j]  (r - 1) * q
+    int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
+};
+
+struct FamMeta {
+    int k, node, r;
+    u32 q, cells;
+    int par[KMAX];
+    u32 rad[KMAX];
+};
+
+// Thread 0 decodes the key.  Parents ascending, first parent most significant; parents with a
+// single state contribute nothing to the index and are dropped.
+__device__ __forceinline__ void decode_family(const u64 *key, int W64, const int *__restrict__ card, FamMeta &m) {
+    m.node = (int)key[0];
+    m.r = card[m.node];
+    int k = 0;
+    u32 q = 1;
+    for (int w = 0; w < W64; ++w) {
+        u64 bits = key[1 + w];
+        while (bits) {
+            int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            int p = w * 64 + b;
+            int c = card[p];
+            if (c > 1 && k < KMAX) {
+                m.par[k] = p;
+                m.rad[k] = (u32)c;
+                q *= (u32)c;
+                ++k;
+            }
+        }
+    }
+    m.k = k;
+    m.q = q;
+    m.cells = q * (u32)m.r;
+}
+
+// cell[b] = cell[b] * rad + state of row b, for the 16 rows held in one 128-bit load.
+__device__ __forceinline__ void radix_step(u32 (&cell)[16], const uint4 &w, u32 rad) {
+    const u32 ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cell[i * 4 + b] = cell[i * 4 + b] * rad + ((ws[i] >> (8 * b)) & 0xffu);
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ void bump(u32 *hist, u32 cell) {
+    atomicAdd(hist + cell, 1u);   // result unused: ATOMS / RED
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ void bump16(u32 *hist, const u32 (&cell)[16], long long row0, long long N) {
+    if (row0 + 16 <= N) {
+#pragma unroll
+        for (int b = 0; b < 16; ++b) bump<GLOBAL>(hist, cell[b]);
+    } else {
+        int nv = (int)(N - row0);
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+            if (b < nv) bump<GLOBAL>(hist, cell[b]);
+    }
+}
+
+// K parents known at compile time: all K+1 column loads of a row group are issued before any
+// is consumed (K+1 independent 16-byte loads in flight per thread).
+template <int K, bool GLOBAL, int THREADS>
+__device__ __forceinline__ void count_rows_k(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                             long long N, long long v0, long long v1, u32 *hist) {
+    const uint8_t *cp[K + 1];
+    u32 rad[K + 1];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
+        uint4 w[K + 1];
+#pragma unroll
+        for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
+        u32 cell[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) cell[b] = 0;
+#pragma unroll
+        for (int a = 0; a <= K; ++a) radix_step(cell, w[a], rad[a]);
+        bump16<GLOBAL>(hist, cell, v * 16, N);
+    }
+}
+
+// Any number of parents (k > 6): columns are walked one at a time.
+template <bool GLOBAL, int THREADS>
+__device__ __forceinline__ void count_rows_any(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                               long long N, long long v0, long long v1, u32 *hist) {
+    const uint8_t *child = data + (long long)m.node * stride;
+    for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
+        u32 cell[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) cell[b] = 0;
+        for (int a = 0; a < m.k; ++a) {
+            uint4 w = ld_stream_v4(data + (long long)m.par[a] * stride + v * 16);
+            radix_step(cell, w, m.rad[a]);
+        }
+        uint4 w = ld_stream_v4(child + v * 16);
+        radix_step(cell, w, (u32)m.r);
+        bump16<GLOBAL>(hist, cell, v * 16, N);
+    }
+}
+
+// Sum over the block in a fixed order (shuffle tree per warp, then warps in index order), so a
+// family's log-likelihood is bit-reproducible run to run and for any slice count.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < THREADS / 32; ++w) t += sh[w];
+    return t;
+}
+
+// k3: sum_{j,x: c>0} c * ln(c / N_ij).  Thread t owns parent configurations t, t+THREADS, ...
+template <int THREADS, bool FROM_GLOBAL>
+__device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh) {
+    double acc = 0.0;
+    for (u32 j = threadIdx.x; j < q; j += THREADS) {
+        const u32 *row = tab + (size_t)j * r;
+        u32 nij = 0;
+        for (int x = 0; x < r; ++x) nij += FROM_GLOBAL ? __ldcg(row + x) : row[x];
+        if (nij) {
+            double dn = (double)nij;
+            for (int x = 0; x < r; ++x) {
+                u32 c = FROM_GLOBAL ? __ldcg(row + x) : row[x];
+                if (c) acc += (double)c * log((double)c / dn);
+            }
+        }
+    }
+    return block_sum<THREADS>(acc, sh);
+}
+
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
+    extern __shared__ u32 s_hist[];
+    __shared__ FamMeta m;
+    __shared__ double s_red[32];
+    __shared__ int s_last;
+
+    const int item = blockIdx.x;
+    const int j = a.jobs[item / a.S];
+    const int slice = item - (item / a.S) * a.S;
+    if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
+    __syncthreads();
+
+    const u32 cells = m.cells;
+    u32 *tab = (a.need && a.need[j]) ? a.arena + a.table_off[j] : nullptr;
+    u32 *hist = GLOBAL ? tab : s_hist;
+    if (!GLOBAL) {
+        for (u32 c = threadIdx.x; c < cells; c += THREADS) s_hist[c] = 0;
+        __syncthreads();
+    }
+
+    const long long nvec = (a.N + 15) >> 4;
+    const long long v0 = nvec * slice / a.S, v1 = nvec * (slice + 1) / a.S;
+    switch (m.k) {
+        case 0: count_rows_k<0, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 1: count_rows_k<1, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 2: count_rows_k<2, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 3: count_rows_k<3, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 4: count_rows_k<4, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 5: count_rows_k<5, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 6: count_rows_k<6, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        default: count_rows_any<GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+    }
+    __syncthreads();
+
+    if (!GLOBAL && tab) {   // merge this slice's shared-memory table into the HBM table
+        for (u32 c = threadIdx.x; c < cells; c += THREADS) {
+            u32 v = s_hist[c];
+            if (v) atomicAdd(tab + c, v);
+        }
+    }
+    if (!a.reduce) return;
+
+    double ll;
+    if (!GLOBAL && a.S == 1) {
+        ll = family_loglik<THREADS, false>(s_hist, m.q, m.r, s_red);
+    } else {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(a.done + j, 1u) == (u32)(a.S - 1));
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        ll = family_loglik<THREADS, true>(tab, m.q, m.r, s_red);
+    }
+    if (threadIdx.x == 0) {
+        a.ll_out[a.key_base + j] = ll;
+        a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
+    }
+}
+
+// k3 alone: reduce HBM tables after the cross-GPU all-reduce (row-sharded datasets).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njobs) {
+    __shared__ FamMeta m;
+    __shared__ double s_red[32];
+    const int j = blockIdx.x;
+    if (j >= njobs) return;
+    if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
+    __syncthreads();
+    double ll = family_loglik<THREADS, true>(a.arena + a.table_off[j], m.q, m.r, s_red);
+    if (threadIdx.x == 0) {
+        a.ll_out[a.key_base + j] = ll;
+        a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
+    }
+}
+
+// Copy one family's table from the arena to the caller's layout (bic_count_families).
+__global__ void k_copy_tables(const u32 *__restrict__ arena, const u64 *__restrict__ table_off,
+                              const u32 *__restrict__ cells_arr, const long long *__restrict__ counts_off,
+                              int *counts_out, Header *hdr) {
+    int f = blockIdx.x;
+    u32 cells = cells_arr[f];
+    if ((long long)cells != counts_off[f + 1] - counts_off[f]) {
+        if (threadIdx.x == 0) atomicOr(&hdr->err, 4u);
+        return;
+    }
+    const u32 *src = arena + table_off[f];
+    int *dst = counts_out + counts_off[f];
+    for (u32 c = threadIdx.x; c < cells; c += blockDim.x) dst[c] = (int)src[c];
+}
+
+}  // namespace bic

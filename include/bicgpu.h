@@ -1,0 +1,151 @@
+/* bicgpu.h — C ABI of libbicgpu.so, the B200 (sm_100a) BIC structure scorer.
+ *
+ * This is the drop-in boundary for the reference's score path
+ *     src/problem/bn/bnlearn.py:27-61          BNLearnWrapper.score()
+ *     src/problem/bn/bnlearn_scripts/bnlearn_score.R:7-40   (Rscript child process)
+ * The reference crosses a *process* boundary per DAG (bnlearn.py:46-54 spawns Rscript and
+ * parses one float from stdout).  A maintainer replaces that subprocess call with the entry
+ * points below (ctypes binding shown in INTEGRATION.md).  Plain pointers and sizes only; no
+ * torch / C++ types; no exception crosses the boundary; every function returns BIC_OK (0) or a
+ * negative bic_status and leaves a message retrievable with bic_last_error().
+ *
+ * Conventions (identical to oracle/bic_oracle.py, which restates bnlearn's discrete BIC):
+ *   - dataset: column-major uint8 state codes, codes[v * stride + row], variable v = v-th
+ *     data column (bnlearn_score.R:29), code < card[v];
+ *   - adjacency: uint8 [B][n][n], adj[b][p][c] != 0  <=>  edge p -> c (row = parent,
+ *     bnlearn.py:44, bnlearn_score.R:35);
+ *   - count table of family (node i, parents P sorted ascending, first most significant):
+ *     cell = j * r_i + x_i,  j = ((x_p1 * r_p2 + x_p2) * r_p3 + ...), int32 counters;
+ *   - score = sum_i [ sum_{jk: N_ijk>0} N_ijk ln(N_ijk / N_ij)  -  pen * (r_i - 1) * q_i ],
+ *     pen = 0.5 ln N (bic), 1 (aic), 0 (loglik); q_i over *declared* cardinalities.
+ *
+ * Pointer arguments are HOST pointers unless BIC_FLAG_DEVICE_PTRS is passed, in which case
+ * every array argument of that call (inputs and outputs) is a device pointer on the context's
+ * GPU.  Pointers are borrowed for the duration of the call.  Calls on one context are
+ * serialised; use one context per GPU (one process per GPU for multi-GPU runs).
+ */
+#ifndef BICGPU_H
+#define BICGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BICGPU_VERSION 100
+
+typedef struct bic_ctx bic_ctx;
+
+typedef enum {
+    BIC_OK = 0,
+    BIC_ERR_CUDA = -1,            /* a CUDA runtime call or kernel failed                    */
+    BIC_ERR_ARG = -2,             /* bad argument (null pointer, n out of range, ...)        */
+    BIC_ERR_NO_DATASET = -3,      /* scoring call before bic_set_dataset                     */
+    BIC_ERR_TABLE_TOO_LARGE = -4, /* a family's q*r exceeds the count-table limit            */
+    BIC_ERR_OOM = -5,             /* device allocation failed                                */
+    BIC_ERR_NCCL = -6,            /* NCCL missing or a collective failed                     */
+    BIC_ERR_BAD_CODE = -7,        /* dataset holds a state code >= its declared cardinality  */
+    BIC_ERR_BAD_FAMILY = -8       /* a parent index is out of range or equals the node       */
+} bic_status;
+
+typedef enum { BIC_METRIC_BIC = 0, BIC_METRIC_LOGLIK = 1, BIC_METRIC_AIC = 2 } bic_metric;
+
+enum {
+    BIC_FLAG_DEVICE_PTRS = 1,    /* array arguments are device pointers                       */
+    BIC_FLAG_NO_CYCLE_CHECK = 2, /* skip the acyclicity check (bnlearn_score.R:35 does check) */
+    BIC_FLAG_NO_CACHE = 4        /* clear the family-score cache before this call             */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int bic_version(void);
+/* Replaces: process start-up of the Rscript child (bnlearn.py:46-54). */
+int bic_create(bic_ctx **out, int device);
+int bic_destroy(bic_ctx *ctx);
+/* Message of the last failing call on ctx (ctx == NULL: last bic_create failure). */
+const char *bic_last_error(const bic_ctx *ctx);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the
+ * context's own stream.  NULL restores the own stream. */
+int bic_set_stream(bic_ctx *ctx, void *cuda_stream);
+int bic_sync(bic_ctx *ctx);
+
+/* ---- dataset ---------------------------------------------------------------------------
+ * Replaces: data(list = dataset_name); dataset <- get(dataset_name)  (bnlearn_score.R:25-26).
+ * codes: uint8 [n][stride] column-major (stride >= N), card: int32 [n] declared cardinalities
+ * (1..255).  The library keeps its own padded copy in HBM and validates codes < card.
+ * Clears the family-score cache. */
+int bic_set_dataset(bic_ctx *ctx, const uint8_t *codes, int64_t N, int32_t n, int64_t stride,
+                    const int32_t *card, int is_device);
+
+/* ---- families --------------------------------------------------------------------------
+ * Replaces: the per-node contingency counting inside bnlearn::score (call site
+ * bnlearn_score.R:38).  Family f = (node[f], parents[parent_off[f] .. parent_off[f+1])).
+ * counts_out receives the dense int32 table of family f at counts_off[f]; counts_off[f+1] -
+ * counts_off[f] must equal q_f * r_f.  Bypasses the cache.  flags: BIC_FLAG_DEVICE_PTRS. */
+int bic_count_families(bic_ctx *ctx, const int32_t *node, const int64_t *parent_off,
+                       const int32_t *parents, int64_t F, const int64_t *counts_off,
+                       int32_t *counts_out, int flags);
+/* One decomposable score term per family (through the family-score cache). */
+int bic_score_families(bic_ctx *ctx, const int32_t *node, const int64_t *parent_off,
+                       const int32_t *parents, int64_t F, int metric, double *out, int flags);
+
+/* ---- DAGs ------------------------------------------------------------------------------
+ * Replaces: BNLearnWrapper.score() end to end (bnlearn.py:38-61 + bnlearn_score.R:7-40) for a
+ * batch of B DAGs.  out[b] = score, or NaN when DAG b is cyclic / has a self loop (the
+ * reference's R child exits non-zero there, bnlearn.py:56-57); *n_invalid (may be NULL)
+ * receives how many were rejected. */
+int bic_score_dags_adj(bic_ctx *ctx, const uint8_t *adj, int64_t B, int metric, double *out,
+                       int64_t *n_invalid, int flags);
+/* Same, parent lists in CSR: family (b, i) has parents[off[b*n+i] .. off[b*n+i+1]);
+ * off has B*n + 1 entries.  For wide networks (n in the hundreds) where B*n*n bytes of
+ * adjacency would dominate. */
+int bic_score_dags_csr(bic_ctx *ctx, const int64_t *off, const int32_t *parents, int64_t B,
+                       int metric, double *out, int64_t *n_invalid, int flags);
+/* Same, the reference's candidate wire format (src/toolkit/labeled.py:116-154): per DAG n
+ * vertex labels (BN variable index of vertex v) and n edge words, bit u of ebits[b][v] set
+ * <=> edge vertex u -> vertex v (u < v); the relabel of bnlearn.py:38-42 runs on the GPU.
+ * n <= 32.  DAGs whose labels are not a permutation of 0..n-1 are rejected like cyclic ones
+ * (bnlearn.py:34-35 asserts). */
+int bic_score_dags_wire(bic_ctx *ctx, const uint8_t *labels, const uint32_t *ebits, int64_t B,
+                        int metric, double *out, int64_t *n_invalid, int flags);
+
+/* ---- family-score cache ---------------------------------------------------------------- */
+typedef struct {
+    int64_t families;      /* distinct (node, parent-set) families held                     */
+    int64_t capacity;      /* families the current allocation can hold                      */
+    int64_t lookups;       /* family instances looked up since creation / last clear        */
+    int64_t misses;        /* of those, how many had to be counted                          */
+    int64_t bytes;         /* device bytes held by table + registry                         */
+} bic_cache_stats_t;
+int bic_cache_clear(bic_ctx *ctx);
+int bic_cache_reserve(bic_ctx *ctx, int64_t families);
+int bic_cache_stats(bic_ctx *ctx, bic_cache_stats_t *out);
+
+/* ---- profiling (CUDA events on the launching stream, around the family-count kernels) --- */
+typedef struct {
+    double count_ms;       /* device time spent in family-count launches                    */
+    int64_t count_launches;/* how many family-count kernels were launched                   */
+    int64_t kernel_launches;/* every kernel this library launched                           */
+    int64_t families_counted;
+    int64_t rows_counted;  /* sum over counted families of N (this rank's rows)             */
+    int64_t alg_bytes;     /* sum over counted families of (k+1)*N + 4*q*r                  */
+} bic_profile_t;
+int bic_profile_enable(bic_ctx *ctx, int on);
+int bic_profile_reset(bic_ctx *ctx);
+int bic_profile_get(bic_ctx *ctx, bic_profile_t *out);
+
+/* ---- row sharding over several GPUs (one process per GPU) ------------------------------
+ * Each rank holds N_rank rows of the same n columns.  After bic_comm_init every scoring call
+ * must be made collectively with identical family / DAG arguments on every rank: partial
+ * count tables are summed with ncclAllReduce(uint32) over NVLink before the fp64 reduce, and
+ * ln N uses the global row count.  NCCL is dlopen()ed ("libnccl.so.2") on first use.
+ * bic_comm_unique_id: rank 0 creates the 128-byte id and ships it to the others (e.g. with
+ * torch.distributed.broadcast). */
+int bic_comm_unique_id(uint8_t id_out[128]);
+int bic_comm_init(bic_ctx *ctx, const uint8_t id[128], int rank, int world);
+int bic_comm_destroy(bic_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BICGPU_H */

@@ -1,0 +1,325 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle and the reference's golden
+values.  Counts are bit-exact; scores agree within 1e-9 relative (BASELINE.json north_star)."""
+import itertools
+import math
+import os
+
+import numpy as np
+import pytest
+
+import dags_vae_search_b200 as pkg
+from dags_vae_search_b200 import synth, wire
+from oracle import bic_oracle as O
+from oracle import c_oracle as C
+from graph_stub import Graph, from_dict_to_graph
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9   # north_star: BIC within 1e-9 relative in fp64
+
+
+def assert_scores(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    rel = np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-300)
+    assert rel.size == 0 or rel.max() <= RTOL, rel.max()
+
+
+def csr_of(families):
+    node = np.array([f[0] for f in families], dtype=np.int32)
+    off = np.zeros(len(families) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(f[1]) for f in families])
+    par = np.array([p for f in families for p in f[1]], dtype=np.int32)
+    return node, off, par
+
+
+def all_families(n, max_k=None):
+    fams = []
+    for i in range(n):
+        others = [p for p in range(n) if p != i]
+        for k in range(0, (n - 1 if max_k is None else max_k) + 1):
+            for ps in itertools.combinations(others, k):
+                fams.append((i, list(ps)))
+    return fams
+
+
+@pytest.fixture(scope="module")
+def asia_scorer(asia):
+    with pkg.BicScorer(*asia) as s:
+        yield s
+
+
+@pytest.fixture(scope="module")
+def sachs_scorer(sachs):
+    with pkg.BicScorer(*sachs) as s:
+        yield s
+
+
+# ------------------------------------------------------------------ reference golden values
+def test_known_answer_through_wrapper(known_answer):
+    # reference tests/problem/bn/test_bnlearn.py:46-55, igraph replaced by a stub of the same API
+    graph = from_dict_to_graph(known_answer["graph_dict"], 8)
+    evaluator = pkg.BNLearnWrapper("asia", "bic")
+    result = evaluator.score(graph)
+    assert isinstance(result, float)
+    assert -13331.093616667435 == pytest.approx(result, abs=1e-5)
+    assert abs(result - known_answer["expected"]) / abs(known_answer["expected"]) < RTOL
+    assert evaluator(graph) == result                      # used as a bare callable (predictors/utils.py:24)
+    assert evaluator.score_batch([graph, graph]).tolist() == [result, result]
+
+
+def test_wrapper_error_conventions():
+    ev = pkg.BNLearnWrapper("asia", "bic")
+    with pytest.raises(AssertionError, match="Expected 8 vertices"):
+        ev.score(Graph(7, [], list(range(7))))
+    with pytest.raises(AssertionError, match="Expected graph labels from 0 to 7"):
+        ev.score(Graph(8, [], [0, 1, 2, 3, 4, 5, 6, 6]))
+    with pytest.raises(Exception, match="R script failed"):   # cyclic: R's amat<- refuses
+        ev.score(Graph(8, [(0, 1), (1, 2), (2, 0)], list(range(8))))
+    # labels permute vertices into variables (bnlearn.py:38-42)
+    g1 = Graph(8, [(0, 1)], [3, 5, 0, 1, 2, 4, 6, 7])
+    g2 = Graph(8, [(3, 5)], list(range(8)))
+    assert ev.score(g1) == ev.score(g2)
+
+
+def test_1408_reference_values(asia_scorer, golden_dir):
+    targets = np.load(os.path.join(golden_dir, "asia_predictor_targets.npy"))
+    d = np.load(os.path.join(golden_dir, "asia_test_dags.npz"))
+    scores = asia_scorer.score_wire(d["labels"], d["ebits"].astype(np.uint32))
+    assert scores.shape == (22022,) and not np.isnan(scores).any()
+    order = np.sort(scores)
+    pos = np.clip(np.searchsorted(order, targets), 1, len(order) - 1)
+    nearest = np.where(np.abs(order[pos] - targets) < np.abs(order[pos - 1] - targets), order[pos], order[pos - 1])
+    assert (np.abs(nearest - targets) / np.abs(targets)).max() < RTOL
+
+
+# ----------------------------------------------------------------------- counts, bit-exact
+def test_asia_all_1024_families_counts_and_scores(asia, asia_scorer):
+    codes, card = asia
+    fams = all_families(8)
+    assert len(fams) == 1024
+    tabs = asia_scorer.count_families([f[0] for f in fams], [f[1] for f in fams])
+    for (i, ps), t in zip(fams, tabs):
+        want = O.family_counts(codes, card, i, ps)
+        assert t.dtype == np.int32 and np.array_equal(t, want), (i, ps)
+    node, off, par = csr_of(fams)
+    for metric in ("bic", "loglik", "aic"):
+        got = asia_scorer.score_families_csr(node, off, par, metric=metric, no_cache=True)
+        want = C.score_families(codes, card, node, off, par, metric=metric)
+        assert_scores(got, want)
+
+
+def test_sachs_families_every_class(sachs, sachs_scorer):
+    """k = 0..10 parents: tables from 3 cells to 3^11 = 177 147 cells, i.e. every count-kernel
+    class including the HBM-atomics one (q*r*4 B > shared memory)."""
+    codes, card = sachs
+    rng = np.random.default_rng(1)
+    fams = []
+    for k in range(0, 11):
+        for _ in range(6 if k < 10 else 3):
+            i = int(rng.integers(11))
+            ps = sorted(rng.choice([p for p in range(11) if p != i], size=k, replace=False).tolist())
+            fams.append((i, ps))
+    tabs = sachs_scorer.count_families([f[0] for f in fams], [f[1] for f in fams])
+    for (i, ps), t in zip(fams, tabs):
+        assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (i, ps)
+        assert t.sum() == 5000
+    node, off, par = csr_of(fams)
+    assert_scores(sachs_scorer.score_families_csr(node, off, par, no_cache=True),
+                  C.score_families(codes, card, node, off, par))
+
+
+# --------------------------------------------------------------------------- DAG batches
+def test_asia_10k_candidates(asia, asia_scorer, golden_dir):
+    codes, card = asia
+    d = np.load(os.path.join(golden_dir, "asia_candidates_10k.npz"))
+    adj = wire.to_adjacency(d["labels"], d["ebits"].astype(np.uint32))
+    true = np.zeros((1, 8, 8), dtype=np.uint8)
+    for u, v in [(0, 2), (1, 3), (1, 4), (2, 5), (3, 5), (5, 6), (5, 7), (4, 7)]:
+        true[0, u, v] = 1
+    adj = np.concatenate([true, adj])
+    want = C.score_dags_adj(codes, card, adj)
+    asia_scorer.cache_clear()
+    got = asia_scorer.score_adjacency(adj)
+    assert_scores(got, want)
+    assert got[0] == pytest.approx(-11109.741872493603, rel=RTOL)
+    st = asia_scorer.cache_stats()
+    assert st["lookups"] == adj.shape[0] * 8 and st["misses"] == st["families"] <= 1024
+    # warm cache, cache off, and the wire-format entry point give the same bits
+    assert np.array_equal(asia_scorer.score_adjacency(adj), got)
+    assert np.array_equal(asia_scorer.score_adjacency(adj, no_cache=True), got)
+    assert np.array_equal(asia_scorer.score_wire(d["labels"], d["ebits"].astype(np.uint32)), got[1:])
+
+
+def test_sachs_100k_candidates(sachs, sachs_scorer, golden_dir):
+    codes, card = sachs
+    d = np.load(os.path.join(golden_dir, "sachs_candidates_100k.npz"))
+    labels, ebits = d["labels"], d["ebits"].astype(np.uint32)
+    got = sachs_scorer.score_wire(labels, ebits, no_cache=True)
+    assert got.shape == (100000,) and not np.isnan(got).any()
+    # oracle on the unique families only (the per-DAG C oracle would recount 1.1 M families)
+    adj = wire.to_adjacency(labels, ebits)
+    masks = (adj.astype(np.int64) << np.arange(11)[None, :, None]).sum(axis=1)     # [B, child] parent bitmask
+    keys = masks * 16 + np.arange(11)[None, :]
+    uniq, inv = np.unique(keys, return_inverse=True)
+    fams = [(int(k % 16), [p for p in range(11) if (k // 16) >> p & 1]) for k in uniq]
+    node, off, par = csr_of(fams)
+    fam_scores = C.score_families(codes, card, node, off, par)
+    want = fam_scores[inv.reshape(keys.shape)]
+    want = np.cumsum(want, axis=1)[:, -1]          # sequential sum in variable order, like the GPU
+    assert_scores(got, want)
+    assert sachs_scorer.cache_stats()["families"] == len(uniq)
+    # adjacency entry point agrees bit for bit
+    assert np.array_equal(sachs_scorer.score_adjacency(adj[:5000]), got[:5000])
+
+
+def test_cyclic_and_invalid_dags(asia_scorer):
+    adj = np.zeros((5, 8, 8), dtype=np.uint8)
+    adj[0, 0, 1] = adj[0, 1, 2] = 1                 # fine
+    adj[1, 0, 1] = adj[1, 1, 2] = adj[1, 2, 0] = 1  # 3-cycle
+    adj[2, 3, 3] = 1                                # self loop
+    adj[3, 6, 7] = adj[3, 7, 6] = 1                 # 2-cycle
+    out, invalid = asia_scorer.score_adjacency(adj, return_invalid=True)
+    assert invalid == 3
+    assert np.isnan(out[[1, 2, 3]]).all() and not np.isnan(out[[0, 4]]).any()
+    labels = np.tile(np.arange(8, dtype=np.uint8), (2, 1))
+    labels[1, 7] = 6                                # not a permutation (bnlearn.py:35)
+    out, invalid = asia_scorer.score_wire(labels, np.zeros((2, 8), dtype=np.uint32), return_invalid=True)
+    assert invalid == 1 and np.isnan(out[1]) and not np.isnan(out[0])
+    with pytest.raises(pkg.BicError, match="BAD_FAMILY"):
+        asia_scorer.score_families([0], [[0]])
+    with pytest.raises(pkg.BicError, match="BAD_FAMILY"):
+        asia_scorer.score_families([0], [[8]])
+
+
+def test_empty_batches(asia_scorer):
+    assert asia_scorer.score_adjacency(np.zeros((0, 8, 8), dtype=np.uint8)).shape == (0,)
+    assert asia_scorer.score_families([], []).shape == (0,)
+    assert asia_scorer.count_families([], []) == []
+
+
+def test_csr_entry_point_matches_adjacency(sachs_scorer):
+    adj = synth.er_candidates(11, 3000, 10, 22, None, seed=9)
+    parents, off = [], [0]
+    for b in range(adj.shape[0]):
+        for i in range(11):
+            ps = np.flatnonzero(adj[b, :, i])
+            parents.extend(ps.tolist())
+            off.append(len(parents))
+    got = sachs_scorer.score_csr(np.array(off), np.array(parents, dtype=np.int32), adj.shape[0])
+    assert np.array_equal(got, sachs_scorer.score_adjacency(adj))
+
+
+def test_device_pointer_entry(asia, asia_scorer):
+    import torch
+    adj = synth.er_candidates(8, 512, 7, 11, None, seed=2)
+    host = asia_scorer.score_adjacency(adj)
+    dev = asia_scorer.score_adjacency(torch.from_numpy(adj).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+    with pkg.BicScorer(torch.from_numpy(asia[0]).cuda(), asia[1]) as s2:
+        assert np.array_equal(s2.score_adjacency(adj), host)
+
+
+# ------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("N", [1, 15, 16, 17, 127, 129, 4097])
+def test_ragged_row_counts(N):
+    rng = np.random.default_rng(N)
+    card = np.array([2, 3, 1, 4, 5], dtype=np.int32)          # includes a constant variable
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    fams = all_families(5)
+    with pkg.BicScorer(codes, card) as s:
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for (i, ps), t in zip(fams, tabs):
+            assert np.array_equal(t, O.family_counts(codes, card, i, ps)), (N, i, ps)
+        node, off, par = csr_of(fams)
+        assert_scores(s.score_families_csr(node, off, par), C.score_families(codes, card, node, off, par))
+
+
+def test_bad_dataset_rejected():
+    codes = np.array([[0, 1, 2, 1]], dtype=np.uint8)
+    with pytest.raises(pkg.BicError, match="BAD_CODE"):
+        pkg.BicScorer(codes, np.array([2], dtype=np.int32))
+    with pytest.raises(pkg.BicError, match="BIC_ERR_ARG"):
+        pkg.BicScorer(codes, np.array([0], dtype=np.int32))
+
+
+def test_table_too_large_is_an_error():
+    rng = np.random.default_rng(0)
+    card = np.full(12, 6, dtype=np.int32)
+    codes = rng.integers(0, 6, size=(12, 1000)).astype(np.uint8)
+    with pkg.BicScorer(codes, card) as s:
+        with pytest.raises(pkg.BicError, match="TABLE_TOO_LARGE"):
+            s.score_families([0], [list(range(1, 12))])       # 6^12 cells
+        assert s.cache_stats()["families"] == 0
+        assert_scores(s.score_families([0], [[1, 2]]), [O.family_score(codes, card, 0, [1, 2])])
+
+
+def test_wide_network_csr_keys(tmp_path):
+    """n = 441 (pigs-shaped): 7-word parent bitmasks, CSR input, in-degree <= 2."""
+    n, N = 441, 20000
+    adj, card, cpts = synth.make_network(n, 592, 2, [3], seed=11)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(3))
+    dags = [adj]
+    rng = np.random.default_rng(4)
+    for _ in range(3):
+        a = adj.copy()
+        for _ in range(10):
+            u, v = rng.choice(n, 2, replace=False)
+            a[u, v] = 0
+        dags.append(a)
+    parents, off = [], [0]
+    for a in dags:
+        for i in range(n):
+            parents.extend(np.flatnonzero(a[:, i]).tolist())
+            off.append(len(parents))
+    with pkg.BicScorer(codes, card) as s:
+        got = s.score_csr(np.array(off), np.array(parents, dtype=np.int32), len(dags))
+        want = C.score_dags_adj(codes, card, np.stack(dags))
+        assert_scores(got, want)
+        assert np.array_equal(s.score_adjacency(np.stack(dags)), got)
+        cyc = adj.copy()
+        order = synth.topo_order(adj)
+        cyc[order[-1], order[0]] = 1
+        ps = np.flatnonzero(adj[:, order[-1]])
+        if len(ps):
+            cyc[order[0], ps[0]] = 1   # make sure first..last are connected: first -> ps[0] -> last -> first
+        out = s.score_adjacency(cyc[None])
+        assert np.isnan(out[0]) == (not O.is_acyclic(cyc))
+
+
+# ------------------------------------------------------------- sliced rows (large N) + props
+def test_large_N_sliced_counts_and_properties():
+    """N = 3 M rows: few families per launch => several row slices per family, merged through
+    HBM tables and reduced by the last slice.  Checked against the C oracle and through
+    size-independent properties (sum of counts, marginalisation, decomposition)."""
+    N = 3_000_000
+    adj, card, cpts = synth.make_network(10, 14, 3, [2, 3, 4], seed=5)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(6))
+    fams = [(0, []), (1, [0]), (2, [0, 1]), (3, [0, 1, 2]), (4, [0, 1, 2, 3]), (5, [0, 1, 2, 3, 4]),
+            (6, [0, 1, 2, 3, 4, 5]), (7, [0, 1, 2, 3, 4, 5, 6]), (9, [1, 2, 3, 4, 5, 6, 7, 8])]
+    with pkg.BicScorer(codes, card) as s:
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for (i, ps), t in zip(fams, tabs):
+            assert t.sum() == N
+            assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (i, ps)
+        # marginalising the last parent out gives the smaller family's table
+        t_big = s.family_counts(4, [0, 1, 2, 3])
+        t_small = s.family_counts(4, [0, 1, 2])
+        r3 = int(card[3])
+        assert np.array_equal(t_big.reshape(-1, r3, int(card[4])).sum(axis=1), t_small)
+        node, off, par = csr_of(fams)
+        got = s.score_families_csr(node, off, par, no_cache=True)
+        assert_scores(got, C.score_families(codes, card, node, off, par))
+        # a DAG's score is the sum of its family terms, in variable order
+        dag = np.zeros((1, 10, 10), dtype=np.uint8)
+        dag[0] = adj
+        fam_terms = s.score_families(list(range(10)), [np.flatnonzero(adj[:, i]).tolist() for i in range(10)])
+        assert s.score_adjacency(dag)[0] == np.cumsum(fam_terms)[-1]
+        # many families in one launch (one slice each) give the same bits as sliced launches
+        many = all_families(10, max_k=2)
+        node, off, par = csr_of(many)
+        batch = s.score_families_csr(node, off, par, no_cache=True)
+        s.cache_clear()
+        single = np.array([s.score_families([i], [ps], no_cache=True)[0] for i, ps in many[:40]])
+        assert np.array_equal(batch[:40], single)

@@ -1,0 +1,150 @@
+"""CPU: the C-ABI library loads and exports what include/bicgpu.h declares; host-side logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import dags_vae_search_b200 as pkg
+from dags_vae_search_b200 import _native as nat
+from dags_vae_search_b200 import dist as bdist
+from dags_vae_search_b200 import synth, wire
+from oracle import bic_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    nat.build()
+    return nat.lib()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "bicgpu.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char \*)\s*(bic_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(nat.SYMBOLS), declared ^ set(nat.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.bic_version() == 100
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", nat.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ctx = ctypes.c_void_p()
+    rc = lib.bic_create(ctypes.byref(ctx), 0)
+    assert rc == -1 and not ctx.value
+    assert b"no CPU fallback" in lib.bic_last_error(None)
+    with pytest.raises(pkg.BicError):
+        pkg.BNLearnWrapper("asia", "bic")
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dags_vae_search_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "liboracle" not in src, f
+
+
+def test_unknown_metric_and_dataset():
+    with pytest.raises(NotImplementedError):
+        pkg.BNLearnWrapper("asia", "bde")
+    with pytest.raises(ValueError):
+        pkg.load_dataset("no_such_dataset")
+    codes, card, names = pkg.load_dataset("asia")
+    assert codes.shape == (8, 5000) and list(card) == [2] * 8 and names == list("ASTLBEXD")
+    codes, card, names = pkg.load_dataset("sachs")
+    assert codes.shape == (11, 5000) and list(card) == [3] * 11
+
+
+def test_csv_loader_matches_sorted_levels(tmp_path):
+    p = tmp_path / "d.csv"
+    p.write_text("A,B\nyes,LOW\nno,HIGH\nyes,AVG\nno,LOW\n")
+    codes, card, names = pkg.load_csv(str(p))
+    assert names == ["A", "B"] and list(card) == [2, 3]
+    assert codes.tolist() == [[1, 0, 1, 0], [2, 1, 0, 2]]
+
+
+def test_wire_roundtrip_against_oracle(known_answer, golden_dir):
+    import pyarrow.parquet as pq
+    d = known_answer["graph_dict"]
+    labels, ebits = wire.pack_dicts([d], 8)
+    assert np.array_equal(wire.to_adjacency(labels, ebits)[0], O.labeled_dict_to_adjacency(d, 8))
+    t = pq.read_table(os.path.join(golden_dir, "labeled_sample.parquet"))
+    labels, ebits = wire.pack_table(t, 8)
+    rows = t.to_pylist()
+    l2, e2 = wire.pack_dicts(rows, 8)
+    assert np.array_equal(labels, l2) and np.array_equal(ebits, e2)
+    adj = wire.to_adjacency(labels, ebits)
+    for b, row in enumerate(rows):
+        assert np.array_equal(adj[b], O.labeled_dict_to_adjacency(row, 8))
+    fixture = np.load(os.path.join(golden_dir, "asia_candidates_10k.npz"))
+    assert np.array_equal(fixture["labels"][:64], labels) and np.array_equal(fixture["ebits"][:64], ebits)
+
+
+def test_synth_candidates_are_dags():
+    adj = synth.er_candidates(12, 200, 11, 26, 4, seed=3)
+    assert adj.shape == (200, 12, 12) and adj.sum(axis=1).max() <= 4
+    assert all(O.is_acyclic(a) for a in adj)
+    net, card, cpts = synth.make_network(12, 20, 4, [2], seed=42)
+    assert net.sum() == 20 and O.is_acyclic(net)
+    codes = synth.forward_sample(net, card, cpts, 5000, np.random.default_rng(1))
+    assert codes.shape == (12, 5000) and codes.max() == 1
+    moves = synth.local_moves(net, 20, 3, 4, seed=5)
+    assert all(O.is_acyclic(a) for a in moves) and moves.sum(axis=1).max() <= 4
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 7, 100, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [bdist.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from dags_vae_search_b200 import dist as bdist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+total = 11
+lo, hi = bdist.shard_range(total, rank, 2)
+full = bdist.gather_scores(np.arange(lo, hi, dtype=np.float64) * -1.5, total)
+assert np.array_equal(full, np.arange(total) * -1.5), full
+uid = bdist.broadcast_unique_id()
+assert len(uid) == 128
+import torch
+t = torch.tensor(list(uid), dtype=torch.int64)
+dist.all_reduce(t)
+assert (t == 2 * torch.tensor(list(uid), dtype=torch.int64)).all()   # both ranks hold the same id
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_candidate_sharding_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o
