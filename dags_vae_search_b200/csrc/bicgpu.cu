@@ -229,10 +229,10 @@ int header_fetch(bic_ctx *c) {
 
 template <int THREADS, bool GLOBAL>
 int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
-    static bool attr_set = false;   // one flag per template instance
-    if (smem > 48 * 1024 && !attr_set) {
+    static size_t attr_smem = 40 * 1024;   // per template instance; static + dynamic over 48 KB needs the opt-in
+    if (smem > attr_smem) {
         CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_smem = smem;
     }
     k_count<THREADS, GLOBAL><<<(unsigned)items, THREADS, smem, c->stream>>>(a); LAUNCH(c);
     CU(cudaGetLastError());
