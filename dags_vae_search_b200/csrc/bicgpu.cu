@@ -266,15 +266,20 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     const bool sharded = c->comm != nullptr;
     const bool all_tables = want_tables || sharded;
 
-    // slices per family: enough CTAs to fill the GPU, but at least 64K rows per slice
+    // Row slices per family.  Two reasons to slice: (a) few families -> enough CTAs to fill the
+    // GPU; (b) a dataset larger than L2 -> items run slice-major, so all resident CTAs sweep the
+    // same window of rows (all n columns of one slice <= L2_WINDOW bytes) and each column
+    // segment comes from HBM once per launch instead of once per family.  Never under 64K rows.
     NeedArgs na;
     na.all = all_tables ? 1 : 0;
     const long long target = (long long)c->sm_count * 8;
     const long long smax = std::max<long long>(1, c->N / 65536);
+    const long long L2_WINDOW = 32ll << 20;
+    const long long s_l2 = ((long long)c->n * c->N + L2_WINDOW - 1) / L2_WINDOW;
     bool any_table = all_tables;
     for (int k = 0; k < NCLASS; ++k) {
         long long cnt = h.class_count[k];
-        long long S = cnt ? std::min(smax, (target + cnt - 1) / cnt) : 1;
+        long long S = cnt ? std::min(smax, std::max(s_l2, (target + cnt - 1) / cnt)) : 1;
         na.S[k] = (int)std::max<long long>(1, S);
         if (cnt && (na.S[k] > 1 || k == 3)) any_table = true;
     }
@@ -318,6 +323,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         if (!cnt) continue;
         a.jobs = c->class_jobs.as<int>() + (long long)k * max_jobs;
         a.S = na.S[k];
+        a.njobs = (int)cnt;
         long long items = cnt * a.S;
         if (items > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
         if (k == 0) TRY((launch_count<256, false>(c, a, items, CLASS0_CELLS * sizeof(u32))));
