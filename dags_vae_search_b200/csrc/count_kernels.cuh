@@ -228,37 +228,42 @@ __device__ __forceinline__ void count_rows_any(const FamMeta &m, const uint8_t *
     }
 }
 
-// Sum over the block in a fixed order (shuffle tree per warp, then warps in index order), so a
-// family's log-likelihood is bit-reproducible run to run and for any slice count.
-template <int THREADS>
+// The fp64 reduce always runs on RED_LANES = 256 virtual lanes, whatever the block size: lane t
+// owns parent configurations t, t+256, ... and the partial sums are combined in a fixed order
+// (shuffle tree per warp, then the 8 warps in index order).  A family's log-likelihood is
+// therefore bit-identical for every kernel class, slice count and for the row-sharded path.
+constexpr int RED_LANES = 256;
+
 __device__ __forceinline__ double block_sum(double v, double *sh) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < RED_LANES) sh[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
     if (threadIdx.x == 0)
-        for (int w = 0; w < THREADS / 32; ++w) t += sh[w];
+        for (int w = 0; w < RED_LANES / 32; ++w) t += sh[w];
     return t;
 }
 
-// k3: sum_{j,x: c>0} c * ln(c / N_ij).  Thread t owns parent configurations t, t+THREADS, ...
-template <int THREADS, bool FROM_GLOBAL>
+// k3: sum_{j,x: c>0} c * ln(c / N_ij).
+template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh) {
     double acc = 0.0;
-    for (u32 j = threadIdx.x; j < q; j += THREADS) {
-        const u32 *row = tab + (size_t)j * r;
-        u32 nij = 0;
-        for (int x = 0; x < r; ++x) nij += FROM_GLOBAL ? __ldcg(row + x) : row[x];
-        if (nij) {
-            double dn = (double)nij;
-            for (int x = 0; x < r; ++x) {
-                u32 c = FROM_GLOBAL ? __ldcg(row + x) : row[x];
-                if (c) acc += (double)c * log((double)c / dn);
+    if (threadIdx.x < RED_LANES) {
+        for (u32 j = threadIdx.x; j < q; j += RED_LANES) {
+            const u32 *row = tab + (size_t)j * r;
+            u32 nij = 0;
+            for (int x = 0; x < r; ++x) nij += FROM_GLOBAL ? __ldcg(row + x) : row[x];
+            if (nij) {
+                double dn = (double)nij;
+                for (int x = 0; x < r; ++x) {
+                    u32 c = FROM_GLOBAL ? __ldcg(row + x) : row[x];
+                    if (c) acc += (double)c * log((double)c / dn);
+                }
             }
         }
     }
-    return block_sum<THREADS>(acc, sh);
+    return block_sum(acc, sh);
 }
 
 template <int THREADS, bool GLOBAL>
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
 
     double ll;
     if (!GLOBAL && a.S == 1) {
-        ll = family_loglik<THREADS, false>(s_hist, m.q, m.r, s_red);
+        ll = family_loglik<false>(s_hist, m.q, m.r, s_red);
     } else {
         __threadfence();
         __syncthreads();
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        ll = family_loglik<THREADS, true>(tab, m.q, m.r, s_red);
+        ll = family_loglik<true>(tab, m.q, m.r, s_red);
     }
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     if (j >= njobs) return;
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
-    double ll = family_loglik<THREADS, true>(a.arena + a.table_off[j], m.q, m.r, s_red);
+    double ll = family_loglik<true>(a.arena + a.table_off[j], m.q, m.r, s_red);
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
         a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
