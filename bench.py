@@ -37,7 +37,13 @@ WORKLOADS = {
                   batch=4096, desc="alarm-shaped synthetic (37 vars, 46 edges, random CPTs), 10M rows"),
     "synthetic_v12_c2": dict(n=12, e=20, indeg=4, cards=[2], rows=100_000, m_lo=11, m_hi=26, cand_indeg=None,
                              batch=4096, desc="synthetic_v12_c2 (12 vars, 2 states), 100k rows"),
+    # configs[0] / configs[1]: the reference's own data and candidate corpora (tests/golden fixtures)
+    "asia": dict(n=8, rows=200_000, batch=10_001, fixture="asia",
+                 desc="asia (n=8): true DAG + 10k reference candidate DAGs, 200k rows sampled from the MLE CPTs of the true DAG"),
+    "sachs": dict(n=11, rows=5_000, batch=100_000, fixture="sachs",
+                  desc="sachs (n=11): 100k reference candidate DAGs per step on data/bn_sachs (5000 rows)"),
 }
+ASIA_TRUE_EDGES = [(0, 2), (1, 3), (1, 4), (2, 5), (3, 5), (5, 6), (5, 7), (4, 7)]   # A->T S->L S->B T->E L->E E->X E->D B->D
 DATA_SEED = 20240
 CAND_SEED = 1234
 
@@ -55,10 +61,54 @@ def parse_args():
     return ap.parse_args()
 
 
+def fixture_dataset(cfg, rows):
+    """asia / sachs: the reference's own rows (bundled codes); asia is re-sampled to `rows` rows
+    from the MLE CPTs of its true DAG (the shipped 'bn_asia_200k' CSV has 5000 rows)."""
+    import dags_vae_search_b200 as pkg
+    from dags_vae_search_b200 import synth
+    codes, card, _ = pkg.load_dataset(cfg["fixture"])
+    if cfg["fixture"] == "asia" and rows != codes.shape[1]:
+        adj = np.zeros((8, 8), dtype=np.uint8)
+        for u, v in ASIA_TRUE_EDGES:
+            adj[u, v] = 1
+        cpts = []
+        for i in range(8):
+            ps = np.flatnonzero(adj[:, i])
+            j = np.zeros(codes.shape[1], dtype=np.int64)
+            for p in ps:
+                j = j * int(card[p]) + codes[p]
+            q = int(np.prod(card[ps])) if len(ps) else 1
+            cnt = np.bincount(j * int(card[i]) + codes[i], minlength=q * int(card[i])).reshape(q, int(card[i])) + 1e-9
+            cpts.append(cnt / cnt.sum(axis=1, keepdims=True))
+        codes = synth.forward_sample(adj, card, cpts, rows, np.random.default_rng(42))
+    elif rows != codes.shape[1]:
+        codes = codes[:, :rows]
+    return None, card, codes
+
+
+def fixture_candidates(cfg, batch):
+    from dags_vae_search_b200 import wire
+    if cfg["fixture"] == "asia":
+        d = np.load(os.path.join(ROOT, "tests", "golden", "asia_candidates_10k.npz"))
+        adj = wire.to_adjacency(d["labels"], d["ebits"].astype(np.uint32))
+        true = np.zeros((1, 8, 8), dtype=np.uint8)
+        for u, v in ASIA_TRUE_EDGES:
+            true[0, u, v] = 1
+        adj = np.concatenate([true, adj])
+    else:
+        d = np.load(os.path.join(ROOT, "tests", "golden", "sachs_candidates_100k.npz"))
+        adj = wire.to_adjacency(d["labels"], d["ebits"].astype(np.uint32))
+    reps = -(-batch // len(adj))
+    return np.ascontiguousarray(np.concatenate([adj] * reps)[:batch])
+
+
 def make_dataset_gpu(cfg, rows, device):
     """Forward-sample the network on the GPU with torch (plumbing, not the product)."""
     import torch
     from dags_vae_search_b200 import synth
+    if "fixture" in cfg:
+        adj, card, codes = fixture_dataset(cfg, rows)
+        return adj, card, torch.from_numpy(codes).to(device)
     adj, card, cpts = synth.make_network(cfg["n"], cfg["e"], cfg["indeg"], cfg["cards"], DATA_SEED)
     gen = torch.Generator(device=device)
     gen.manual_seed(DATA_SEED)
@@ -79,6 +129,8 @@ def make_dataset_gpu(cfg, rows, device):
 
 def make_dataset_cpu(cfg, rows):
     from dags_vae_search_b200 import synth
+    if "fixture" in cfg:
+        return fixture_dataset(cfg, rows)
     adj, card, cpts = synth.make_network(cfg["n"], cfg["e"], cfg["indeg"], cfg["cards"], DATA_SEED)
     codes = synth.forward_sample(adj, card, cpts, rows, np.random.default_rng(DATA_SEED))
     return adj, card, codes
@@ -86,6 +138,8 @@ def make_dataset_cpu(cfg, rows):
 
 def candidate_batch(cfg, batch, step, rank, world):
     from dags_vae_search_b200 import synth
+    if "fixture" in cfg:      # the reference's corpus: the same batch every step (cache is cleared anyway)
+        return fixture_candidates(cfg, batch)
     return synth.er_candidates(cfg["n"], batch, cfg["m_lo"], cfg["m_hi"], cfg["cand_indeg"],
                                seed=CAND_SEED + step * world + rank)
 
@@ -270,13 +324,27 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = prof["alg_bytes"] / (prof["count_ms"] * 1e-3) / 1e9 if prof["count_ms"] > 0 else 0.0
+    # roofline of the dominant kernel = the count-kernel class that took most of the step
+    kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory)",
+               "k_count<512,false> (tables <= 12288 cells in shared memory)",
+               "k_count<512,false> (tables <= 49152 cells in shared memory)",
+               "k_count<256,true> (tables in HBM, L2 atomics)"]
+    dom = int(np.argmax(prof["class_ms"]))
+    dom_ms, dom_launches = prof["class_ms"][dom], max(prof["class_launches"][dom], 1)
+    achieved = prof["class_alg_bytes"][dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and not args.rows and not args.batch:
+        t = json.load(open(tpath)).get(args.workload, {}).get(str(dom))
+        if t:
+            traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
     line = {
         "metric": "BIC-scored DAGs/sec", "value": dags / (ms_res * 1e-3), "unit": "DAGs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts + f64 reduce", "data": "synthetic",
         "config": {"workload": cfg["desc"], "rows": rows, "n": n, "dags_per_step_per_gpu": batch,
-                   "candidates": f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step",
+                   "candidates": (f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step"
+                                  if "fixture" not in cfg else "reference encoder_dataset corpus (tests/golden), same batch every step"),
                    "cache": "family-score cache cleared at the start of every step (cold)",
                    "l2": f"dataset {rows * n / 1e6:.0f} MB streamed per family; inputs larger than L2" if rows * n > 126e6 else "dataset fits L2",
                    "parallelism": f"candidate-sharded x{world}, dataset replicated"},
@@ -286,8 +354,12 @@ def main():
         "family_count_rows_per_sec": prof["rows_counted"] / (prof["count_ms"] * 1e-3) if prof["count_ms"] > 0 else None,
         "families_counted_per_step": prof["families_counted"] / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_count (family count + fused fp64 reduce)",
-                     "launches": prof["count_launches"], "count_ms_per_step": prof["count_ms"] / args.steps,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernels[dom],
+                     "launches": dom_launches, "ms_per_launch": dom_ms / dom_launches,
+                     "alg_bytes_per_launch": prof["class_alg_bytes"][dom] / dom_launches,
+                     "families_per_launch": prof["class_families"][dom] / dom_launches,
+                     "share_of_step": dom_ms / ms_res, "all_count_kernels_ms_per_step": prof["count_ms"] / args.steps,
+                     "all_count_kernels_gbs": prof["alg_bytes"] / (prof["count_ms"] * 1e-3) / 1e9 if prof["count_ms"] > 0 else None,
                      "peak_source": peak_src, "rank": 0},
         "clocks": clocks,
         "checksum": checksum,

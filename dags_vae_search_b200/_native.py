@@ -52,7 +52,9 @@ class CacheStats(ctypes.Structure):
 class Profile(ctypes.Structure):
     _fields_ = [("count_ms", ctypes.c_double), ("count_launches", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_int64), ("families_counted", ctypes.c_int64),
-                ("rows_counted", ctypes.c_int64), ("alg_bytes", ctypes.c_int64)]
+                ("rows_counted", ctypes.c_int64), ("alg_bytes", ctypes.c_int64),
+                ("class_ms", ctypes.c_double * 4), ("class_launches", ctypes.c_int64 * 4),
+                ("class_families", ctypes.c_int64 * 4), ("class_alg_bytes", ctypes.c_int64 * 4)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

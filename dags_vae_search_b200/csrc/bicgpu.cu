@@ -117,7 +117,8 @@ struct bic_ctx {
     // profiling
     bool prof_on = false;
     bic_profile_t prof = {};
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_used;
+    struct EvPair { cudaEvent_t a, b; int cls; };
+    std::vector<EvPair> ev_pool, ev_used;
 
     // row sharding
     nccl_comm comm = nullptr;
@@ -307,17 +308,6 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.ll_out = ll_out; a.np_out = np_out;
     a.reduce = sharded ? 0 : 1;
 
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->prof_on) {
-        if (c->ev_pool.empty()) {
-            CU(cudaEventCreate(&e0));
-            CU(cudaEventCreate(&e1));
-        } else {
-            e0 = c->ev_pool.back().first; e1 = c->ev_pool.back().second;
-            c->ev_pool.pop_back();
-        }
-        CU(cudaEventRecord(e0, c->stream));
-    }
     for (int k = 0; k < NCLASS; ++k) {
         long long cnt = h.class_count[k];
         if (!cnt) continue;
@@ -326,18 +316,37 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         a.njobs = (int)cnt;
         long long items = cnt * a.S;
         if (items > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
-        if (k == 0) TRY((launch_count<256, false>(c, a, items, CLASS0_CELLS * sizeof(u32))));
-        if (k == 1) TRY((launch_count<512, false>(c, a, items, CLASS1_CELLS * sizeof(u32))));
-        if (k == 2) TRY((launch_count<512, false>(c, a, items, CLASS2_CELLS * sizeof(u32))));
+        bic_ctx::EvPair ev = {nullptr, nullptr, k};
+        if (c->prof_on) {   // CUDA events on the launching stream, one pair per count launch
+            if (c->ev_pool.empty()) {
+                CU(cudaEventCreate(&ev.a));
+                CU(cudaEventCreate(&ev.b));
+            } else {
+                ev = c->ev_pool.back();
+                ev.cls = k;
+                c->ev_pool.pop_back();
+            }
+            CU(cudaEventRecord(ev.a, c->stream));
+        }
+        // shared memory per CTA: class 0 gets 4x its largest table so that tables <= 256 cells
+        // run with 32 bank-interleaved lane replicas (conflict-free atomics)
+        const u32 cap[NCLASS] = {CLASS0_WORDS, CLASS1_CELLS, CLASS2_CELLS, 0};
+        a.cap_words = cap[k];
+        if (k == 0) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
+        if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32))));
+        if (k == 2) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 3) TRY((launch_count<256, true>(c, a, items, 0)));
-    }
-    if (c->prof_on) {
-        CU(cudaEventRecord(e1, c->stream));
-        c->ev_used.push_back({e0, e1});
+        if (c->prof_on) {
+            CU(cudaEventRecord(ev.b, c->stream));
+            c->ev_used.push_back(ev);
+        }
+        c->prof.class_launches[k] += 1;
+        c->prof.class_families[k] += cnt;
+        c->prof.class_alg_bytes[k] += (long long)h.alg_bytes[k];
+        c->prof.alg_bytes += (long long)h.alg_bytes[k];
     }
     c->prof.families_counted += njobs;
     c->prof.rows_counted += njobs * c->N;
-    c->prof.alg_bytes += (long long)h.alg_bytes;
 
     if (sharded) {
         size_t cells = (size_t)c->h_hdr->table_cells;
@@ -398,7 +407,10 @@ int finish_call(bic_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     for (auto &p : c->ev_used) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->prof.count_ms += ms;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->prof.count_ms += ms;
+            c->prof.class_ms[p.cls] += ms;
+        }
         c->ev_pool.push_back(p);
     }
     c->ev_used.clear();
@@ -558,7 +570,7 @@ int bic_destroy(bic_ctx *c) {
     if (c->d_card) cudaFree(c->d_card);
     if (c->d_hdr) cudaFree(c->d_hdr);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
-    for (auto &p : c->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return BIC_OK;

@@ -301,7 +301,7 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
     int cls = cells <= CLASS0_CELLS ? 0 : cells <= CLASS1_CELLS ? 1 : cells <= CLASS2_CELLS ? 2 : 3;
     u32 pos = atomicAdd(&hdr->class_count[cls], 1u);
     class_jobs[(long long)cls * max_jobs + pos] = (int)j;
-    atomicAdd(&hdr->alg_bytes, (u64)(k + 1) * (u64)N + 4ull * cells);
+    atomicAdd(&hdr->alg_bytes[cls], (u64)(k + 1) * (u64)N + 4ull * cells);
 }
 
 // Owners of PENDING entries take id = base + rank, publish their key in the registry and

@@ -19,6 +19,7 @@ constexpr u64 MAX_CELLS = 1ull << 28;      // q*r limit of one count table (1 Gi
 // memory (one privatised histogram per CTA), class 3 counts straight into HBM with L2 atomics.
 constexpr int NCLASS = 4;
 constexpr u32 CLASS0_CELLS = 2048;         //   8 KB of int32 -> many CTAs per SM
+constexpr u32 CLASS0_WORDS = 8192;         //  32 KB per class-0 CTA: room for lane replicas (count_kernels.cuh)
 constexpr u32 CLASS1_CELLS = 12288;        //  48 KB
 constexpr u32 CLASS2_CELLS = 49152;        // 192 KB (one CTA per SM)
 
@@ -29,7 +30,7 @@ struct Header {
     u32 err;                   // bit 0: q*r over MAX_CELLS; bit 1: bad parent index
     u32 n_invalid;             // DAGs rejected (cyclic, self loop, labels not a permutation)
     u32 pad;
-    u64 alg_bytes;             // sum (k+1)*N + 4*q*r over the new families
+    u64 alg_bytes[NCLASS];     // sum (k+1)*N + 4*q*r over the new families, per class
     u64 table_cells;           // cells of all count tables that must live in HBM (scan total)
 };
 

@@ -26,6 +26,7 @@ struct CountArgs {
     const int *jobs;         // job ids of this launch (one class)
     int njobs;               // how many
     int S;                   // row slices per family
+    u32 cap_words;           // shared-memory words available to one CTA's table(s)
     u32 *arena;              // HBM count tables
     const u32 *need;         // per job: cells if its table lives in HBM, else 0 (nullable)
     const u64 *table_off;    // per job: offset into arena (valid where need != 0)
@@ -38,6 +39,8 @@ struct CountArgs {
 struct FamMeta {
     int k, node, r;
     u32 q, cells;
+    u32 R;      // lane replicas of the shared-memory table (power of two, <= 32)
+    u32 mul;    // byte offset of a cell = cell * mul  (mul = 4 * R)
     int par[KMAX];
     u32 rad[KMAX];
 };
@@ -74,15 +77,23 @@ __device__ __forceinline__ void decode_family(const u64 *key, int W64, const int
 // mixed-radix index is built on packed lanes so that one IMAD (FMA pipe) advances several rows
 // at once and the per-row byte extraction (ALU pipe, the measured bottleneck of the first
 // version: 77 % ALU, 60 % DRAM) happens once per row instead of once per row per column:
-//   MODE_U8  (cells <= 64):     8-bit lanes, 4 rows per register, no unpack at all;
-//   MODE_U16 (cells <= 16383): 16-bit lanes, 2 rows per register, bytes unpacked with PRMT;
-//   MODE_U32 (anything else):   one register per row.
-// The packed modes carry the index pre-multiplied by 4, i.e. as the byte offset of the int32
-// counter, so the extracted lane feeds the shared-memory atomic directly.
+//   MODE_U8  (cells <= 64):        8-bit lanes, 4 rows per register, no unpack at all;
+//   MODE_U16 (cells*R <= 16383): 16-bit lanes, 2 rows per register, bytes unpacked with PRMT,
+//                                 index pre-multiplied by `mul` so the extracted lane is the
+//                                 byte offset that feeds the shared-memory atomic directly;
+//   MODE_U32 (anything else):     one register per row.
+//
+// Lane replicas.  After the arithmetic moved to packed lanes the limiter became the shared-
+// memory data pipe: 2.2 wavefronts per warp atomic, 54 % of them bank conflicts between
+// different cells (ncu, profiles/r01b).  Small tables are therefore kept in R bank-interleaved
+// replicas, slot = cell * R + (lane % R): with R = 32 lane l only ever touches bank l, so a
+// warp atomic is one wavefront whatever the data; R = 16/8/4/2 cut conflicts proportionally.
+// Replicas are summed once, after the row loop.
 enum { MODE_U8 = 0, MODE_U16 = 1, MODE_U32 = 2 };
+constexpr int REPL_MAX_PER_THREAD = 16;   // replicated tables hold at most 16 cells per thread (compact_replicas)
 
-__device__ __forceinline__ int count_mode(u32 cells) {
-    return cells <= 64u ? MODE_U8 : cells <= 16383u ? MODE_U16 : MODE_U32;
+__device__ __forceinline__ int count_mode(u32 cells, u32 R) {
+    return cells <= 64u ? MODE_U8 : cells * R <= 16383u ? MODE_U16 : MODE_U32;
 }
 
 template <bool GLOBAL>
@@ -105,7 +116,7 @@ __device__ __forceinline__ void bump16(u32 *hist, const u32 (&off)[16], long lon
 }
 
 template <int K>
-__device__ __forceinline__ void cells_u8(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 (&off)[16]) {
+__device__ __forceinline__ void cells_u8(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 mul, u32 (&off)[16]) {
     u32 acc[4] = {w[0].x, w[0].y, w[0].z, w[0].w};
 #pragma unroll
     for (int a = 1; a <= K; ++a) {
@@ -114,15 +125,13 @@ __device__ __forceinline__ void cells_u8(const uint4 (&w)[K + 1], const u32 (&ra
         for (int i = 0; i < 4; ++i) acc[i] = acc[i] * rad[a] + ws[i];   // 4 rows per IMAD, lanes stay < 64
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        u32 a4 = acc[i] * 4u;                                            // lanes <= 252
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) off[i * 4 + b] = __byte_perm(a4, 0u, 0x4440u + b);
-    }
+        for (int b = 0; b < 4; ++b) off[i * 4 + b] = __byte_perm(acc[i], 0u, 0x4440u + b) * mul;
 }
 
 template <int K>
-__device__ __forceinline__ void cells_u16(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 (&off)[16]) {
+__device__ __forceinline__ void cells_u16(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 mul, u32 (&off)[16]) {
     u32 acc[8];
 #pragma unroll
     for (int a = 0; a <= K; ++a) {
@@ -142,14 +151,14 @@ __device__ __forceinline__ void cells_u16(const uint4 (&w)[K + 1], const u32 (&r
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        u32 a4 = acc[i] * 4u;                            // lanes <= 65532
+        u32 a4 = acc[i] * mul;                           // lanes <= 65532
         off[2 * i] = a4 & 0xffffu;
         off[2 * i + 1] = a4 >> 16;
     }
 }
 
 template <int K>
-__device__ __forceinline__ void cells_u32(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 (&off)[16]) {
+__device__ __forceinline__ void cells_u32(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 mul, u32 (&off)[16]) {
 #pragma unroll
     for (int b = 0; b < 16; ++b) off[b] = 0;
 #pragma unroll
@@ -161,7 +170,7 @@ __device__ __forceinline__ void cells_u32(const uint4 (&w)[K + 1], const u32 (&r
             for (int b = 0; b < 4; ++b) off[i * 4 + b] = off[i * 4 + b] * rad[a] + ((ws[i] >> (8 * b)) & 0xffu);
     }
 #pragma unroll
-    for (int b = 0; b < 16; ++b) off[b] *= 4u;
+    for (int b = 0; b < 16; ++b) off[b] *= mul;
 }
 
 // K parents known at compile time: all K+1 column loads of a row group are issued before any
@@ -178,14 +187,15 @@ __device__ __forceinline__ void count_rows_k(const FamMeta &m, const uint8_t *__
     }
     cp[K] = data + (long long)m.node * stride;
     rad[K] = (u32)m.r;
+    const u32 mul = m.mul;
     for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
         uint4 w[K + 1];
 #pragma unroll
         for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
         u32 off[16];
-        if (MODE == MODE_U8) cells_u8<K>(w, rad, off);
-        else if (MODE == MODE_U16) cells_u16<K>(w, rad, off);
-        else cells_u32<K>(w, rad, off);
+        if (MODE == MODE_U8) cells_u8<K>(w, rad, mul, off);
+        else if (MODE == MODE_U16) cells_u16<K>(w, rad, mul, off);
+        else cells_u32<K>(w, rad, mul, off);
         bump16<GLOBAL>(hist, off, v * 16, N);
     }
 }
@@ -197,7 +207,7 @@ __device__ __forceinline__ void count_rows_mode(const FamMeta &m, const uint8_t 
         count_rows_k<K, MODE_U32, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist);
         return;
     }
-    switch (count_mode(m.cells)) {
+    switch (count_mode(m.cells, m.R)) {
         case MODE_U8: count_rows_k<K, MODE_U8, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist); break;
         case MODE_U16: count_rows_k<K, MODE_U16, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist); break;
         default: count_rows_k<K, MODE_U32, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist); break;
@@ -223,9 +233,33 @@ __device__ __forceinline__ void count_rows_any(const FamMeta &m, const uint8_t *
                 for (int b = 0; b < 4; ++b) off[i * 4 + b] = off[i * 4 + b] * rad + ((ws[i] >> (8 * b)) & 0xffu);
         }
 #pragma unroll
-        for (int b = 0; b < 16; ++b) off[b] *= 4u;
+        for (int b = 0; b < 16; ++b) off[b] *= m.mul;
         bump16<GLOBAL>(hist, off, v * 16, N);
     }
+}
+
+// Sum the R lane replicas of every cell into hist[0 .. cells).  Thread t owns cells t,
+// t+THREADS, ...; sums are parked in registers across the barrier because the compacted table
+// overlaps the replicated one.  Replica order is rotated by the thread index so the R reads of
+// a warp fall into different banks.
+template <int THREADS>
+__device__ __forceinline__ void compact_replicas(u32 *hist, u32 cells, u32 R) {
+    u32 loc[REPL_MAX_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < REPL_MAX_PER_THREAD; ++i) {
+        u32 c = threadIdx.x + i * THREADS;
+        u32 s = 0;
+        if (c < cells)
+            for (u32 r = 0; r < R; ++r) s += hist[c * R + ((r + threadIdx.x) & (R - 1))];
+        loc[i] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < REPL_MAX_PER_THREAD; ++i) {
+        u32 c = threadIdx.x + i * THREADS;
+        if (c < cells) hist[c] = loc[i];
+    }
+    __syncthreads();
 }
 
 // The fp64 reduce always runs on RED_LANES = 256 virtual lanes, whatever the block size: lane t
@@ -281,15 +315,29 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     __syncthreads();
 
     const u32 cells = m.cells;
+    const long long nvec = (a.N + 15) >> 4;
+    const long long v0 = nvec * slice / a.S, v1 = nvec * (slice + 1) / a.S;
+    if (threadIdx.x == 0) {
+        // replicas pay off only when the row loop dwarfs zeroing + summing R tables
+        u32 R = 1;
+        if (!GLOBAL && (v1 - v0) * 16 >= 65536)
+            while (R < 32 && cells * (R * 2) <= a.cap_words && cells <= (u32)(REPL_MAX_PER_THREAD * THREADS)) R *= 2;
+        // measured (ncu source counters, tools/microbench2): R = 32 -> 1.00 wavefront per warp
+        // atomic, 16 -> 2.0, none -> ~2.6, but 8 -> 2.8 and 4 -> 3.3 because interleaving then
+        // confines each lane to 4 or 8 banks.  So: 32, 16 or nothing.
+        if (R < 16) R = 1;
+        m.R = R;
+        m.mul = 4u * R;
+    }
+    __syncthreads();
+    const u32 R = m.R;
     u32 *tab = (a.need && a.need[j]) ? a.arena + a.table_off[j] : nullptr;
-    u32 *hist = GLOBAL ? tab : s_hist;
+    u32 *hist = GLOBAL ? tab : s_hist + (threadIdx.x & (R - 1));
     if (!GLOBAL) {
-        for (u32 c = threadIdx.x; c < cells; c += THREADS) s_hist[c] = 0;
+        for (u32 c = threadIdx.x; c < cells * R; c += THREADS) s_hist[c] = 0;
         __syncthreads();
     }
 
-    const long long nvec = (a.N + 15) >> 4;
-    const long long v0 = nvec * slice / a.S, v1 = nvec * (slice + 1) / a.S;
     switch (m.k) {
         case 0: count_rows_mode<0, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
         case 1: count_rows_mode<1, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
@@ -301,6 +349,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         default: count_rows_any<GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
     }
     __syncthreads();
+    if (!GLOBAL && R > 1) compact_replicas<THREADS>(s_hist, cells, R);
 
     if (!GLOBAL && tab) {   // merge this slice's shared-memory table into the HBM table
         for (u32 c = threadIdx.x; c < cells; c += THREADS) {

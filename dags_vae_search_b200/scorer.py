@@ -237,7 +237,11 @@ class BicScorer:
     def profile(self) -> dict:
         p = nat.Profile()
         self._check(self._lib.bic_profile_get(self._ctx, ctypes.byref(p)))
-        return {k: (float(getattr(p, k)) if k == "count_ms" else int(getattr(p, k))) for k, _ in nat.Profile._fields_}
+        out = {}
+        for k, _ in nat.Profile._fields_:
+            v = getattr(p, k)
+            out[k] = list(v) if hasattr(v, "__len__") else (float(v) if k == "count_ms" else int(v))
+        return out
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         self._check(self._lib.bic_set_stream(self._ctx, ctypes.c_void_p(cuda_stream or 0)))

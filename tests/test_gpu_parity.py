@@ -323,3 +323,42 @@ def test_large_N_sliced_counts_and_properties():
         s.cache_clear()
         single = np.array([s.score_families([i], [ps], no_cache=True)[0] for i, ps in many[:40]])
         assert np.array_equal(batch[:40], single)
+
+
+# ------------------------------------------------------ BASELINE.json full size (config 4)
+def test_alarm_shaped_full_size_10M_rows():
+    """configs[3]: 37 variables, 10 M rows (the bench workload).  Oracle on a handful of families
+    and DAGs (seconds), plus size-independent properties over a whole candidate batch."""
+    import torch
+    import bench
+    cfg = bench.WORKLOADS["alarm"]
+    N = cfg["rows"]
+    true_adj, card, codes_t = bench.make_dataset_gpu(cfg, N, torch.device("cuda", 0))
+    codes = codes_t.cpu().numpy()
+    with pkg.BicScorer(codes_t, card) as s:
+        del codes_t
+        rng = np.random.default_rng(0)
+        fams = []
+        for k in (0, 1, 2, 3, 4, 5, 6):
+            i = int(rng.integers(37))
+            fams.append((i, sorted(rng.choice([p for p in range(37) if p != i], size=k, replace=False).tolist())))
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for (i, ps), t in zip(fams, tabs):
+            assert t.sum() == N
+            assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (i, ps)
+        # marginalisation: dropping the last parent of the k=4 family
+        i, ps = fams[4]
+        small = s.family_counts(i, ps[:-1])
+        assert np.array_equal(tabs[4].reshape(-1, int(card[ps[-1]]), int(card[i])).sum(axis=1), small)
+        # a batch of candidates: cold == warm == no-cache bits; true DAG beats its neighbours' mean
+        cand = bench.candidate_batch(cfg, 512, 0, 0, 1)
+        cold = s.score_adjacency(cand, no_cache=True)
+        warm = s.score_adjacency(cand)
+        assert np.array_equal(cold, warm) and not np.isnan(cold).any()
+        want = C.score_dags_adj(codes, card, np.concatenate([true_adj[None], cand[:3]]))
+        got = s.score_adjacency(np.concatenate([true_adj[None], cand[:3]]))
+        assert_scores(got, want)
+        assert got[0] > cold.mean()
+        # decomposition: DAG score == sum of its family terms in variable order
+        terms = s.score_families(list(range(37)), [np.flatnonzero(cand[7][:, v]).tolist() for v in range(37)])
+        assert cold[7] == np.cumsum(terms)[-1]
