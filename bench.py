@@ -37,6 +37,11 @@ WORKLOADS = {
                   batch=4096, desc="alarm-shaped synthetic (37 vars, 46 edges, random CPTs), 10M rows"),
     "synthetic_v12_c2": dict(n=12, e=20, indeg=4, cards=[2], rows=100_000, m_lo=11, m_hi=26, cand_indeg=None,
                              batch=4096, desc="synthetic_v12_c2 (12 vars, 2 states), 100k rows"),
+    # configs[4]: rows sharded over the GPUs (12.5 M rows per GPU; 8 GPUs = 100 M rows), NCCL count all-reduce
+    "diabetes": dict(n=413, e=602, indeg=2, cards=list(range(3, 22)), rows=12_500_000, batch=64, row_sharded=True,
+                     desc="diabetes-shaped synthetic (413 vars, 602 edges, r in [3,21]), 12.5M rows per GPU, row-sharded"),
+    "pigs": dict(n=441, e=592, indeg=2, cards=[3], rows=12_500_000, batch=64, row_sharded=True,
+                 desc="pigs-shaped synthetic (441 vars, 592 edges, r = 3), 12.5M rows per GPU, row-sharded"),
     # configs[0] / configs[1]: the reference's own data and candidate corpora (tests/golden fixtures)
     "asia": dict(n=8, rows=200_000, batch=10_001, fixture="asia",
                  desc="asia (n=8): true DAG + 10k reference candidate DAGs, 200k rows sampled from the MLE CPTs of the true DAG"),
@@ -102,8 +107,9 @@ def fixture_candidates(cfg, batch):
     return np.ascontiguousarray(np.concatenate([adj] * reps)[:batch])
 
 
-def make_dataset_gpu(cfg, rows, device):
-    """Forward-sample the network on the GPU with torch (plumbing, not the product)."""
+def make_dataset_gpu(cfg, rows, device, shard=0):
+    """Forward-sample the network on the GPU with torch (plumbing, not the product).  `shard`
+    offsets the sampling seed: row-sharded ranks hold different rows of the same network."""
     import torch
     from dags_vae_search_b200 import synth
     if "fixture" in cfg:
@@ -111,7 +117,7 @@ def make_dataset_gpu(cfg, rows, device):
         return adj, card, torch.from_numpy(codes).to(device)
     adj, card, cpts = synth.make_network(cfg["n"], cfg["e"], cfg["indeg"], cfg["cards"], DATA_SEED)
     gen = torch.Generator(device=device)
-    gen.manual_seed(DATA_SEED)
+    gen.manual_seed(DATA_SEED + 7919 * shard)
     codes = torch.zeros((cfg["n"], rows), dtype=torch.uint8, device=device)
     chunk = 1 << 22
     for i in synth.topo_order(adj):
@@ -140,6 +146,10 @@ def candidate_batch(cfg, batch, step, rank, world):
     from dags_vae_search_b200 import synth
     if "fixture" in cfg:      # the reference's corpus: the same batch every step (cache is cleared anyway)
         return fixture_candidates(cfg, batch)
+    if cfg.get("row_sharded"):   # true DAG + local-search neighbours; identical on every rank
+        true_adj, _, _ = synth.make_network(cfg["n"], cfg["e"], cfg["indeg"], cfg["cards"], DATA_SEED)
+        moves = synth.local_moves(true_adj, batch - 1, 3, 3, seed=CAND_SEED + step)
+        return np.concatenate([true_adj[None], moves])
     return synth.er_candidates(cfg["n"], batch, cfg["m_lo"], cfg["m_hi"], cfg["cand_indeg"],
                                seed=CAND_SEED + step * world + rank)
 
@@ -268,24 +278,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    true_adj, card, codes = make_dataset_gpu(cfg, rows, device)
+    sharded = bool(cfg.get("row_sharded"))
+    true_adj, card, codes = make_dataset_gpu(cfg, rows, device, shard=rank if sharded else 0)
     scorer = pkg.BicScorer(codes, card, device=local_rank)
+    del codes
+    torch.cuda.empty_cache()
     scorer.set_stream(torch.cuda.current_stream().cuda_stream)
     n = cfg["n"]
+    if sharded and world > 1:
+        from dags_vae_search_b200 import dist as bdist
+        bdist.init_row_sharding(scorer)
 
     total_steps = args.warmup + args.steps
-    host_adj = [torch.from_numpy(candidate_batch(cfg, batch, s, rank, world)).pin_memory() for s in range(total_steps)]
-    dev_adj = [a.to(device) for a in host_adj]
     dev_out = torch.empty(batch, dtype=torch.float64, device=device)
     host_out = torch.empty(batch, dtype=torch.float64).pin_memory()
+    if sharded:   # wide network: parent lists in CSR instead of B*n*n bytes of adjacency
+        def to_csr(adj):
+            b, p, c = np.nonzero(adj.transpose(0, 2, 1))      # sorted by (dag, child, parent)
+            counts = np.bincount(b * n + p, minlength=adj.shape[0] * n)
+            off = np.zeros(adj.shape[0] * n + 1, dtype=np.int64)
+            np.cumsum(counts, out=off[1:])
+            return torch.from_numpy(off).pin_memory(), torch.from_numpy(c.astype(np.int32)).pin_memory()
+        host_csr = [to_csr(candidate_batch(cfg, batch, s, 0, 1)) for s in range(total_steps)]
+        dev_csr = [(o.to(device), p.to(device)) for o, p in host_csr]
+        h2d_bytes = int(np.mean([o.numel() * 8 + p.numel() * 4 for o, p in host_csr]))
 
-    def step_resident(s):
-        scorer.cache_clear()
-        return scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
+        def step_resident(s):
+            scorer.cache_clear()
+            return scorer.score_csr_into(dev_csr[s][0].data_ptr(), dev_csr[s][1].data_ptr(), batch, dev_out.data_ptr(), device=True)
 
-    def step_e2e(s):
-        scorer.cache_clear()
-        return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False)
+        def step_e2e(s):
+            scorer.cache_clear()
+            return scorer.score_csr_into(host_csr[s][0].data_ptr(), host_csr[s][1].data_ptr(), batch, host_out.data_ptr(), device=False)
+    else:
+        host_adj = [torch.from_numpy(candidate_batch(cfg, batch, s, rank, world)).pin_memory() for s in range(total_steps)]
+        dev_adj = [a.to(device) for a in host_adj]
+        h2d_bytes = batch * n * n
+
+        def step_resident(s):
+            scorer.cache_clear()
+            return scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
+
+        def step_e2e(s):
+            scorer.cache_clear()
+            return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False)
 
     def timed(step_fn):
         for s in range(args.warmup):
@@ -318,7 +354,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    dags = batch * world * args.steps
+    if "fixture" in cfg:
+        cand_desc = "reference encoder_dataset corpus (tests/golden), same batch every step"
+    elif sharded:
+        cand_desc = "true DAG + local-search neighbours (<= 3 edge moves each), fresh batch every step, CSR parent lists"
+    else:
+        cand_desc = f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step"
+    dags = batch * (1 if sharded else world) * args.steps   # row-sharded ranks score the same DAGs together
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
@@ -343,12 +385,12 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts + f64 reduce", "data": "synthetic",
         "config": {"workload": cfg["desc"], "rows": rows, "n": n, "dags_per_step_per_gpu": batch,
-                   "candidates": (f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step"
-                                  if "fixture" not in cfg else "reference encoder_dataset corpus (tests/golden), same batch every step"),
+                   "candidates": cand_desc,
                    "cache": "family-score cache cleared at the start of every step (cold)",
                    "l2": f"dataset {rows * n / 1e6:.0f} MB streamed per family; inputs larger than L2" if rows * n > 126e6 else "dataset fits L2",
-                   "parallelism": f"candidate-sharded x{world}, dataset replicated"},
-        "e2e": {"value": dags / (ms_e2e * 1e-3), "unit": "DAGs/s", "h2d_bytes_per_step": batch * n * n,
+                   "parallelism": (f"row-sharded x{world} ({rows} rows per GPU, {rows * world} in total), ncclAllReduce(uint32) of count tables"
+                                   if sharded else f"candidate-sharded x{world}, dataset replicated")},
+        "e2e": {"value": dags / (ms_e2e * 1e-3), "unit": "DAGs/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": batch * 8},
         "gpu_launches": prof["kernel_launches"],
         "family_count_rows_per_sec": prof["rows_counted"] / (prof["count_ms"] * 1e-3) if prof["count_ms"] > 0 else None,
@@ -360,13 +402,17 @@ def main():
                      "families_per_launch": prof["class_families"][dom] / dom_launches,
                      "share_of_step": dom_ms / ms_res, "all_count_kernels_ms_per_step": prof["count_ms"] / args.steps,
                      "all_count_kernels_gbs": prof["alg_bytes"] / (prof["count_ms"] * 1e-3) / 1e9 if prof["count_ms"] > 0 else None,
+                     "classes": [{"kernel": kernels[k].split(" ")[0], "launches": prof["class_launches"][k],
+                                  "families": prof["class_families"][k], "ms": prof["class_ms"][k],
+                                  "gbs": prof["class_alg_bytes"][k] / (prof["class_ms"][k] * 1e-3) / 1e9}
+                                 for k in range(4) if prof["class_ms"][k] > 0],
                      "peak_source": peak_src, "rank": 0},
         "clocks": clocks,
         "checksum": checksum,
     }
     if world == 1 and not args.no_cpu_baseline:
-        codes_host = codes.cpu().numpy()
-        rate, threads, sample, dt = cpu_oracle_rate(codes_host, card, host_adj[args.warmup].numpy())
+        codes_host = make_dataset_gpu(cfg, rows, device)[2].cpu().numpy()   # same seed -> same rows as the scorer holds
+        rate, threads, sample, dt = cpu_oracle_rate(codes_host, card, candidate_batch(cfg, batch, args.warmup, 0, 1))
         line["cpu_baseline"] = {"value": rate, "unit": "DAGs/s", "cores": threads, "kind": "port",
                                 "sample": f"first {sample} candidate DAGs of one step ({dt:.1f} s), no family cache (reference recounts every family)"}
     print(json.dumps(line), flush=True)

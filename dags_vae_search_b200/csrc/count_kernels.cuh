@@ -318,10 +318,14 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     const long long nvec = (a.N + 15) >> 4;
     const long long v0 = nvec * slice / a.S, v1 = nvec * (slice + 1) / a.S;
     if (threadIdx.x == 0) {
-        // replicas pay off only when the row loop dwarfs zeroing + summing R tables
+        // replicas pay off only when the row loop dwarfs zeroing + summing R tables:
+        // at least 16 rows per replicated counter
         u32 R = 1;
-        if (!GLOBAL && (v1 - v0) * 16 >= 65536)
-            while (R < 32 && cells * (R * 2) <= a.cap_words && cells <= (u32)(REPL_MAX_PER_THREAD * THREADS)) R *= 2;
+        const long long rows_here = (v1 - v0) * 16;
+        if (!GLOBAL)
+            while (R < 32 && cells * (R * 2) <= a.cap_words && cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) &&
+                   (long long)cells * (R * 2) * 16 <= rows_here)
+                R *= 2;
         // measured (ncu source counters, tools/microbench2): R = 32 -> 1.00 wavefront per warp
         // atomic, 16 -> 2.0, none -> ~2.6, but 8 -> 2.8 and 4 -> 3.3 because interleaving then
         // confines each lane to 4 or 8 banks.  So: 32, 16 or nothing.

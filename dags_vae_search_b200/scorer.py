@@ -184,6 +184,14 @@ class BicScorer:
                                                  ctypes.byref(inv), self._flags(check_acyclic, no_cache, device)))
         return int(inv.value)
 
+    def score_csr_into(self, off_ptr: int, parents_ptr: int, B: int, out_ptr: int, device: bool,
+                       metric: Optional[str] = None, check_acyclic: bool = True, no_cache: bool = False) -> int:
+        """Raw-pointer CSR variant (int64 offsets [B*n+1], int32 parents)."""
+        inv = ctypes.c_int64(0)
+        self._check(self._lib.bic_score_dags_csr(self._ctx, off_ptr, parents_ptr, B, self._metric(metric), out_ptr,
+                                                 ctypes.byref(inv), self._flags(check_acyclic, no_cache, device)))
+        return int(inv.value)
+
     def score_csr(self, off, parents, B: int, metric: Optional[str] = None, check_acyclic: bool = True,
                   no_cache: bool = False, return_invalid: bool = False):
         """Parent lists in CSR: family (b, i) = parents[off[b*n+i] : off[b*n+i+1]]."""
