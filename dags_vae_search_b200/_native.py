@@ -17,6 +17,7 @@ BIC_OK = 0
 FLAG_DEVICE_PTRS = 1
 FLAG_NO_CYCLE_CHECK = 2
 FLAG_NO_CACHE = 4
+FLAG_NO_DERIVE = 8
 METRICS = {"bic": 0, "loglik": 1, "aic": 2}
 
 STATUS_NAMES = {
@@ -54,7 +55,8 @@ class Profile(ctypes.Structure):
                 ("kernel_launches", ctypes.c_int64), ("families_counted", ctypes.c_int64),
                 ("rows_counted", ctypes.c_int64), ("alg_bytes", ctypes.c_int64),
                 ("class_ms", ctypes.c_double * 4), ("class_launches", ctypes.c_int64 * 4),
-                ("class_families", ctypes.c_int64 * 4), ("class_alg_bytes", ctypes.c_int64 * 4)]
+                ("class_families", ctypes.c_int64 * 4), ("class_alg_bytes", ctypes.c_int64 * 4),
+                ("families_derived", ctypes.c_int64)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

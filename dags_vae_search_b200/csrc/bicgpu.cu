@@ -111,7 +111,8 @@ struct bic_ctx {
 
     // per-sub-batch workspace
     DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
-    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll;
+    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_x, derived_list;
+    bool derive_on = true;   // marginalise tables from counted supersets when the dataset is large
     Header *d_hdr = nullptr, *h_hdr = nullptr;
 
     // profiling
@@ -262,10 +263,13 @@ int refresh_ntotal(bic_ctx *c) {
 // Count (and reduce) `njobs` families described in c->cells_arr / c->class_jobs; the header in
 // pinned memory holds the class counts.  keys/key_base select registry or key buffer.
 int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, long long max_jobs,
-              double *ll_out, double *np_out, bool want_tables) {
+              double *ll_out, double *np_out, bool want_tables, bool with_donors) {
     const Header &h = *c->h_hdr;
     const bool sharded = c->comm != nullptr;
-    const bool all_tables = want_tables || sharded;
+    const u32 n_derived = with_donors ? h.n_derived : 0;
+    u32 lvl_count[DERIVE_LEVELS];
+    for (int l = 0; l < DERIVE_LEVELS; ++l) lvl_count[l] = with_donors ? h.lvl_count[l] : 0;   // header is re-fetched below
+    const bool all_tables = want_tables || sharded || n_derived > 0;
 
     // Row slices per family.  Two reasons to slice: (a) few families -> enough CTAs to fill the
     // GPU; (b) a dataset larger than L2 -> items run slice-major, so all resident CTAs sweep the
@@ -307,9 +311,14 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.done = c->done.as<u32>();
     a.ll_out = ll_out; a.np_out = np_out;
     a.reduce = sharded ? 0 : 1;
+    a.donor = with_donors ? c->donor.as<int>() : nullptr;
+    a.donor_x = with_donors ? c->donor_x.as<int>() : nullptr;
+    u32 class_count[NCLASS];
+    u64 class_alg[NCLASS];
+    for (int k = 0; k < NCLASS; ++k) { class_count[k] = h.class_count[k]; class_alg[k] = h.alg_bytes[k]; }
 
     for (int k = 0; k < NCLASS; ++k) {
-        long long cnt = h.class_count[k];
+        long long cnt = class_count[k];
         if (!cnt) continue;
         a.jobs = c->class_jobs.as<int>() + (long long)k * max_jobs;
         a.S = na.S[k];
@@ -342,11 +351,12 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         }
         c->prof.class_launches[k] += 1;
         c->prof.class_families[k] += cnt;
-        c->prof.class_alg_bytes[k] += (long long)h.alg_bytes[k];
-        c->prof.alg_bytes += (long long)h.alg_bytes[k];
+        c->prof.class_alg_bytes[k] += (long long)class_alg[k];
+        c->prof.alg_bytes += (long long)class_alg[k];
     }
-    c->prof.families_counted += njobs;
-    c->prof.rows_counted += njobs * c->N;
+    c->prof.families_counted += njobs - n_derived;
+    c->prof.rows_counted += (njobs - n_derived) * c->N;
+    c->prof.families_derived += n_derived;
 
     if (sharded) {
         size_t cells = (size_t)c->h_hdr->table_cells;
@@ -355,6 +365,13 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
             if (rc != 0) return fail(c, BIC_ERR_NCCL, std::string("ncclAllReduce(count tables): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
         }
         k_reduce_tables<256><<<(unsigned)njobs, 256, 0, c->stream>>>(a, (int)njobs); LAUNCH(c);
+        CU(cudaGetLastError());
+    }
+    if (n_derived) {   // tables of the counted families are complete: marginalise, most parents first
+        for (int l = DERIVE_LEVELS - 1; l >= 0; --l) {
+            if (!lvl_count[l]) continue;
+            k_derive<256><<<n_derived, 256, 0, c->stream>>>(a, c->derived_list.as<int>(), l); LAUNCH(c);
+        }
         CU(cudaGetLastError());
     }
     return BIC_OK;
@@ -369,7 +386,7 @@ int check_header_err(bic_ctx *c) {
 }
 
 // keys of T instances sit in c->keybuf: look them up, insert + count the unseen families.
-int resolve_instances(bic_ctx *c, long long T, int n_per_dag) {
+int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     TRY(cache_ensure(c, T));
     CU(c->inst.ensure((size_t)T * sizeof(int)));
     CU(c->flag.ensure((size_t)T * sizeof(u32)));
@@ -381,9 +398,18 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag) {
                                       (u32)(c->table_cap - 1), c->regkeys, c->inst.as<int>()); LAUNCH(c);
     k_owner_flags<<<g, 256, 0, c->stream>>>(c->inst.as<int>(), c->table, T, c->flag.as<u32>()); LAUNCH(c);
     TRY((scan_excl<u32, u32>(c, c->flag.as<u32>(), T, c->rank.as<u32>(), &c->d_hdr->f_new, c->bsum32)));
-    k_finalize<<<g, 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->W64, T, c->inst.as<int>(), c->flag.as<u32>(),
-                                         c->rank.as<u32>(), c->reg_count, c->regkeys, c->table, c->d_card, c->N,
-                                         (u32)T, c->d_hdr, c->cells_arr.as<u32>(), c->class_jobs.as<int>()); LAUNCH(c);
+    k_finalize<<<g, 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->Wk, T, c->inst.as<int>(), c->flag.as<u32>(),
+                                         c->rank.as<u32>(), c->reg_count, c->regkeys, c->table); LAUNCH(c);
+    // new families: find superset donors (large datasets only), then describe / classify
+    CU(c->donor.ensure((size_t)T * sizeof(int)));
+    CU(c->donor_x.ensure((size_t)T * sizeof(int)));
+    CU(c->derived_list.ensure((size_t)T * sizeof(int)));
+    const int derive = (c->derive_on && !no_derive && c->N >= (1ll << 20)) ? 1 : 0;
+    k_find_donor<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
+                                           c->d_card, c->n, derive, c->donor.as<int>(), c->donor_x.as<int>()); LAUNCH(c);
+    k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
+                                             c->donor.as<int>(), c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
+                                             c->derived_list.as<int>()); LAUNCH(c);
     CU(cudaGetLastError());
     TRY(header_fetch(c));
     long long f_new = c->h_hdr->f_new;
@@ -395,7 +421,7 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag) {
         return rc;
     }
     if (f_new) {
-        rc = run_count(c, c->regkeys, c->reg_count, f_new, T, c->reg_ll, c->reg_np, false);
+        rc = run_count(c, c->regkeys, c->reg_count, f_new, T, c->reg_ll, c->reg_np, false, true);
         if (rc != BIC_OK) { cache_clear(c); return rc; }
         c->reg_count += f_new;
     }
@@ -500,7 +526,7 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
                                                                              c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
         }
         CU(cudaGetLastError());
-        TRY(resolve_instances(c, T, n));
+        TRY(resolve_instances(c, T, n, (flags & BIC_FLAG_NO_DERIVE) != 0));
         invalid += c->h_hdr->n_invalid;
         double *d_out = out + b0;
         if (!dev) {
@@ -564,7 +590,8 @@ int bic_destroy(bic_ctx *c) {
     cache_free(c);
     DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
                       &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
-                      &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll};
+                      &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_x,
+                      &c->derived_list};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
     if (c->d_card) cudaFree(c->d_card);
@@ -667,7 +694,7 @@ int bic_count_families(bic_ctx *c, const int32_t *node, const int64_t *parent_of
     CU(cudaGetLastError());
     TRY(header_fetch(c));
     TRY(check_header_err(c));
-    TRY(run_count(c, c->keybuf.as<u64>(), 0, F, F, c->tmp_ll.as<double>(), c->tmp_ll.as<double>() + F, true));
+    TRY(run_count(c, c->keybuf.as<u64>(), 0, F, F, c->tmp_ll.as<double>(), c->tmp_ll.as<double>() + F, true, false));
     int *d_out = counts_out;
     if (!dev) {
         CU(c->out_stage.ensure((size_t)std::max<long long>(cells_total, 1) * sizeof(int)));
@@ -713,7 +740,7 @@ int bic_score_families(bic_ctx *c, const int32_t *node, const int64_t *parent_of
         TRY(header_reset(c));
         k_keys_csr<<<nblk(Fc, 256), 256, 0, c->stream>>>(d_off, d_par, d_node, Fc, c->n, c->W64, c->keybuf.as<u64>(), nullptr, c->d_hdr); LAUNCH(c);
         CU(cudaGetLastError());
-        TRY(resolve_instances(c, Fc, 0));
+        TRY(resolve_instances(c, Fc, 0, (flags & BIC_FLAG_NO_DERIVE) != 0));
         double *d_out = out + f0;
         if (!dev) {
             CU(c->out_stage.ensure((size_t)Fc * sizeof(double)));

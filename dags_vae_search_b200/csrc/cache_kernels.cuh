@@ -305,21 +305,96 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
 }
 
 // Owners of PENDING entries take id = base + rank, publish their key in the registry and
-// finalise the table entry; then describe the new family as job `rank`.
-__global__ void k_finalize(const u64 *__restrict__ keybuf, int W64, long long T, int *inst,
+// finalise the table entry.
+__global__ void k_finalize(const u64 *__restrict__ keybuf, int Wk, long long T, int *inst,
                            const u32 *__restrict__ flag, const u32 *__restrict__ rank, long long base,
-                           u64 *regkeys, u32 *table, const int *__restrict__ card, long long N,
-                           u32 max_jobs, Header *hdr, u32 *cells_arr, int *class_jobs) {
+                           u64 *regkeys, u32 *table) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T || !flag[t]) return;
-    int Wk = W64 + 1;
-    u32 j = rank[t];
-    long long id = base + j;
+    long long id = base + rank[t];
     const u64 *key = keybuf + t * Wk;
     for (int w = 0; w < Wk; ++w) regkeys[id * Wk + w] = key[w];
     table[-2 - inst[t]] = (u32)(id + 1);
     inst[t] = (int)id;
-    describe_family(key, W64, card, N, j, max_jobs, hdr, cells_arr, class_jobs);
+}
+
+// Read-only lookup of a key among the finalised entries.
+__device__ __forceinline__ long long cache_find(const u64 *key, int Wk, const u32 *__restrict__ table, u32 mask,
+                                                const u64 *__restrict__ regkeys) {
+    u32 s = (u32)hash_key(key, Wk) & mask;
+    while (true) {
+        u32 e = table[s];
+        if (e == ENT_EMPTY) return -1;
+        long long id = (long long)e - 1;
+        if (keys_equal(key, regkeys + id * Wk, Wk)) return id;
+        s = (s + 1) & mask;
+    }
+}
+
+// Donor search.  Counts are additive over a parent's states, so the table of family (i, P) is
+// the table of (i, P + {x}) summed over x — no pass over the rows.  For every new family look
+// for a *new* family of the same node with exactly one more parent (its table exists in this
+// sub-batch); among several pick the cheapest (smallest cardinality of x, then smallest x),
+// which makes the choice — like the ids — independent of thread timing.
+__global__ void k_find_donor(const u64 *__restrict__ regkeys, int W64, long long base, const Header *hdr,
+                             const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, int n,
+                             int enable, int *donor, int *donor_x) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hdr->f_new) return;
+    donor[j] = -1;
+    donor_x[j] = -1;
+    if (!enable) return;
+    int Wk = W64 + 1;
+    u64 key[W64MAX + 1];
+    const u64 *mine = regkeys + (base + j) * Wk;
+    int pc = 0;
+    for (int w = 0; w < Wk; ++w) key[w] = mine[w];
+    for (int w = 1; w < Wk; ++w) pc += __popcll(key[w]);
+    if (pc >= DERIVE_LEVELS - 1) return;
+    int node = (int)key[0];
+    int best_card = 1 << 30;
+    for (int x = 0; x < n; ++x) {
+        if (x == node || card[x] < 2 || card[x] >= best_card) continue;
+        u64 bit = 1ull << (x & 63);
+        if (key[1 + (x >> 6)] & bit) continue;
+        key[1 + (x >> 6)] |= bit;
+        long long id = cache_find(key, Wk, table, mask, regkeys);
+        key[1 + (x >> 6)] &= ~bit;
+        if (id >= base) {
+            best_card = card[x];
+            donor[j] = (int)(id - base);
+            donor_x[j] = x;
+        }
+    }
+}
+
+// Describe the new families: counted ones get a count job, derived ones go to the derive list.
+__global__ void k_describe_new(const u64 *__restrict__ regkeys, int W64, long long base, const int *__restrict__ card,
+                               long long N, u32 max_jobs, Header *hdr, const int *__restrict__ donor,
+                               u32 *cells_arr, int *class_jobs, int *derived_list) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hdr->f_new) return;
+    const u64 *key = regkeys + (base + j) * (W64 + 1);
+    if (donor[j] < 0) {
+        describe_family(key, W64, card, N, (u32)j, max_jobs, hdr, cells_arr, class_jobs);
+        return;
+    }
+    // derived: its table is smaller than its donor's, which passed the size check
+    u64 cells = (u64)card[(int)key[0]];
+    int pc = 0;
+    for (int w = 0; w < W64; ++w) {
+        u64 m = key[1 + w];
+        pc += __popcll(m);
+        while (m) {
+            int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            cells *= (u64)card[w * 64 + b];
+            if (cells > MAX_CELLS) cells = MAX_CELLS;
+        }
+    }
+    cells_arr[j] = (u32)cells;
+    derived_list[atomicAdd(&hdr->n_derived, 1u)] = (int)j;
+    atomicAdd(&hdr->lvl_count[pc], 1u);
 }
 
 // Cache-bypassing path (bic_count_families): every listed family is job t.

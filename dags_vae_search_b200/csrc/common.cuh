@@ -14,6 +14,7 @@ constexpr int W64MAX = NMAX / 64;          // bitmask words per parent set
 constexpr u32 ENT_EMPTY = 0u;              // hash-table entry: empty
 constexpr u32 ENT_PENDING = 0x80000000u;   // entry = PENDING | instance index while a batch is being deduplicated
 constexpr u64 MAX_CELLS = 1ull << 28;      // q*r limit of one count table (1 GiB of int32)
+constexpr int DERIVE_LEVELS = 32;          // families with fewer parents than this may be derived from a superset
 
 // Count-kernel classes by table size (cells = q*r).  Classes 0..2 keep the table in shared
 // memory (one privatised histogram per CTA), class 3 counts straight into HBM with L2 atomics.
@@ -32,6 +33,8 @@ struct Header {
     u32 pad;
     u64 alg_bytes[NCLASS];     // sum (k+1)*N + 4*q*r over the new families, per class
     u64 table_cells;           // cells of all count tables that must live in HBM (scan total)
+    u32 n_derived;             // new families whose table is marginalised from a counted superset
+    u32 lvl_count[DERIVE_LEVELS];   // of those, by number of parents
 };
 
 __device__ __forceinline__ u64 mix64(u64 x) {

@@ -34,6 +34,8 @@ struct CountArgs {
     double *ll_out;          // [key_base + j]
     double *np_out;          // [key_base + j]  (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
+    const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
+    const int *donor_x;      // per job: the parent summed out of the donor
 };
 
 struct FamMeta {
@@ -388,9 +390,57 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     __shared__ double s_red[32];
     const int j = blockIdx.x;
     if (j >= njobs) return;
+    if (a.donor && a.donor[j] >= 0) return;   // derived families are reduced by k_derive
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
     double ll = family_loglik<true>(a.arena + a.table_off[j], m.q, m.r, s_red);
+    if (threadIdx.x == 0) {
+        a.ll_out[a.key_base + j] = ll;
+        a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
+    }
+}
+
+// Derived families: table(i, P)[j_hi, lo] = sum over the states of x of table(i, P + {x})
+// [(j_hi * r_x + x) * L + lo], L = product of the radices after x (parents > x, then the
+// child).  One CTA per derived family; levels (number of parents) run high to low so a donor that
+// is itself derived is complete.  Then the usual fp64 reduce.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__restrict__ derived_list, int level) {
+    __shared__ FamMeta m;
+    __shared__ double s_red[32];
+    __shared__ u32 s_L, s_rx;
+    __shared__ int s_go;
+    const int j = derived_list[blockIdx.x];
+    if (threadIdx.x == 0) {
+        const u64 *key = a.keys + (a.key_base + j) * (long long)(a.W64 + 1);
+        int pc = 0;
+        for (int w = 0; w < a.W64; ++w) pc += __popcll(key[1 + w]);
+        s_go = (pc == level);
+        if (s_go) {
+            decode_family(key, a.W64, a.card, m);
+            int x = a.donor_x[j];
+            u32 L = (u32)m.r;
+            for (int p = 0; p < m.k; ++p)
+                if (m.par[p] > x) L *= m.rad[p];
+            s_L = L;
+            s_rx = (u32)a.card[x];
+        }
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const u32 *dt = a.arena + a.table_off[a.donor[j]];
+    u32 *mt = a.arena + a.table_off[j];
+    const u32 L = s_L, rx = s_rx, cells = m.cells;
+    for (u32 t = threadIdx.x; t < cells; t += THREADS) {
+        u32 hi = t / L, lo = t - hi * L;
+        const u32 *src = dt + (size_t)hi * rx * L + lo;
+        u32 s = 0;
+        for (u32 xv = 0; xv < rx; ++xv) s += __ldcg(src + (size_t)xv * L);
+        mt[t] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    double ll = family_loglik<true>(mt, m.q, m.r, s_red);
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
         a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;

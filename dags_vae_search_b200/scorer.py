@@ -122,7 +122,7 @@ class BicScorer:
                        metric: Optional[str] = None, no_cache: bool = False) -> np.ndarray:
         node, off, flat = _family_csr(nodes, parent_lists)
         out = np.zeros(len(node), dtype=np.float64)
-        flags = nat.FLAG_NO_CACHE if no_cache else 0
+        flags = (nat.FLAG_NO_CACHE if no_cache else 0) | (0 if self.derive else nat.FLAG_NO_DERIVE)
         self._check(self._lib.bic_score_families(self._ctx, node.ctypes.data, off.ctypes.data, flat.ctypes.data,
                                                  len(node), self._metric(metric), out.ctypes.data, flags))
         return out
@@ -135,7 +135,7 @@ class BicScorer:
         if parents.size == 0:
             parents = np.zeros(1, dtype=np.int32)
         out = np.zeros(len(node), dtype=np.float64)
-        flags = nat.FLAG_NO_CACHE if no_cache else 0
+        flags = (nat.FLAG_NO_CACHE if no_cache else 0) | (0 if self.derive else nat.FLAG_NO_DERIVE)
         self._check(self._lib.bic_score_families(self._ctx, node.ctypes.data, off.ctypes.data, parents.ctypes.data,
                                                  len(node), self._metric(metric), out.ctypes.data, flags))
         return out
@@ -147,10 +147,12 @@ class BicScorer:
             raise NotImplementedError(f"metric {m!r}: only {sorted(nat.METRICS)} are implemented")
         return nat.METRICS[m]
 
-    @staticmethod
-    def _flags(check_acyclic: bool, no_cache: bool, device: bool) -> int:
+    #: set to False to count every family from the rows (no marginalisation from supersets)
+    derive = True
+
+    def _flags(self, check_acyclic: bool, no_cache: bool, device: bool) -> int:
         return ((0 if check_acyclic else nat.FLAG_NO_CYCLE_CHECK) | (nat.FLAG_NO_CACHE if no_cache else 0)
-                | (nat.FLAG_DEVICE_PTRS if device else 0))
+                | (nat.FLAG_DEVICE_PTRS if device else 0) | (0 if self.derive else nat.FLAG_NO_DERIVE))
 
     def score_adjacency(self, adj, metric: Optional[str] = None, check_acyclic: bool = True,
                         no_cache: bool = False, return_invalid: bool = False):

@@ -54,7 +54,9 @@ typedef enum { BIC_METRIC_BIC = 0, BIC_METRIC_LOGLIK = 1, BIC_METRIC_AIC = 2 } b
 enum {
     BIC_FLAG_DEVICE_PTRS = 1,    /* array arguments are device pointers                       */
     BIC_FLAG_NO_CYCLE_CHECK = 2, /* skip the acyclicity check (bnlearn_score.R:35 does check) */
-    BIC_FLAG_NO_CACHE = 4        /* clear the family-score cache before this call             */
+    BIC_FLAG_NO_CACHE = 4,       /* clear the family-score cache before this call             */
+    BIC_FLAG_NO_DERIVE = 8       /* count every new family from the rows, even when its table  *
+                                  * could be marginalised from a counted superset family       */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -136,6 +138,7 @@ typedef struct {
     int64_t class_launches[4];
     int64_t class_families[4];
     int64_t class_alg_bytes[4];
+    int64_t families_derived; /* new families whose table was marginalised from a superset's  */
 } bic_profile_t;
 int bic_profile_enable(bic_ctx *ctx, int on);
 int bic_profile_reset(bic_ctx *ctx);

@@ -47,3 +47,22 @@ def test_row_and_candidate_sharding_world2():
            "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tests", "_multigpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "multigpu ok 2" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_row_sharded_with_derived_families_world1():
+    import ctypes
+    n, N = 8, 1_100_000
+    adj, card, cpts = synth.make_network(n, 10, 3, [2, 3], seed=31)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(32))
+    dags = synth.er_candidates(n, 300, 7, 16, 5, seed=33)
+    with pkg.BicScorer(codes, card) as s:
+        s.derive = False
+        plain = s.score_adjacency(dags, no_cache=True)
+        s.derive = True
+        buf = (ctypes.c_uint8 * 128)()
+        assert nat.lib().bic_comm_unique_id(ctypes.addressof(buf)) == 0
+        s.init_row_sharding(0, 1, bytes(buf))
+        s.profile_reset()
+        sharded = s.score_adjacency(dags, no_cache=True)
+        assert s.profile()["families_derived"] > 0
+        assert np.array_equal(sharded, plain)

@@ -362,3 +362,36 @@ def test_alarm_shaped_full_size_10M_rows():
         # decomposition: DAG score == sum of its family terms in variable order
         terms = s.score_families(list(range(37)), [np.flatnonzero(cand[7][:, v]).tolist() for v in range(37)])
         assert cold[7] == np.cumsum(terms)[-1]
+
+
+# ------------------------------------------- tables marginalised from counted supersets
+def test_derived_families_match_counted_ones():
+    """On large datasets a new family whose superset (one more parent) is counted in the same
+    batch gets its table by summing the superset's table over that parent.  Integer sums: the
+    scores must be bit-identical to counting every family from the rows, and match the oracle."""
+    N = 1_200_000
+    adj, card, cpts = synth.make_network(9, 12, 3, [2, 3, 4, 1], seed=21)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(22))
+    # nested parent sets of node 0 and 5 -> chains of donors, plus unrelated families
+    fams = [(0, []), (0, [1]), (0, [1, 2]), (0, [1, 2, 3]), (0, [1, 2, 3, 4]), (0, [2, 3]), (0, [3]),
+            (5, [0, 8]), (5, [0, 6, 8]), (5, [0, 1, 6, 8]), (5, [8]), (7, [6]), (7, [2, 6]), (4, [0, 1, 2, 3, 5, 6])]
+    node, off, par = csr_of(fams)
+    with pkg.BicScorer(codes, card) as s:
+        s.profile_reset()
+        derived = s.score_families_csr(node, off, par, no_cache=True)
+        prof = s.profile()
+        assert prof["families_derived"] >= 6 and prof["families_counted"] + prof["families_derived"] == len(fams)
+        s.derive = False
+        s.profile_reset()
+        counted = s.score_families_csr(node, off, par, no_cache=True)
+        assert s.profile()["families_derived"] == 0
+        assert np.array_equal(derived, counted)
+        assert_scores(derived, C.score_families(codes, card, node, off, par))
+        # DAG batches: random candidates, derive on/off identical bits
+        s.derive = True
+        dags = synth.er_candidates(9, 600, 8, 20, 5, seed=23)
+        a = s.score_adjacency(dags, no_cache=True)
+        s.derive = False
+        b = s.score_adjacency(dags, no_cache=True)
+        assert np.array_equal(a, b)
+        assert_scores(a[:40], C.score_dags_adj(codes, card, dags[:40]))
