@@ -242,7 +242,9 @@ def run_reference(args, cfg, rows, batch):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts + f64 reduce",
         "data": "synthetic",
-        "config": {"workload": cfg["desc"], "rows": rows, "dags_per_step": sample, "cache": "none (reference recounts every family)"},
+        "config": {"workload": cfg["desc"], "rows": rows, "n": cfg["n"], "dags_per_step_per_gpu": batch,
+                   "dags_timed_per_step": sample, "cache": "none (the reference recounts every family of every DAG)",
+                   "parallelism": f"{threads} host threads over (DAG, node) pairs"},
         "cpu_baseline": {"value": value, "unit": "DAGs/s", "cores": threads, "kind": "port",
                          "sample": f"first {sample} of {batch} candidate DAGs of each step, all {cfg['n']} families recounted per DAG"},
         "e2e": {"value": value, "unit": "DAGs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -367,7 +369,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # roofline of the dominant kernel = the count-kernel class that took most of the step
-    kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory)",
+    kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory, lane replicas <= 512 cells)",
                "k_count<512,false> (tables <= 12288 cells in shared memory)",
                "k_count<512,false> (tables <= 49152 cells in shared memory)",
                "k_count<256,true> (tables in HBM, L2 atomics)"]
