@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -113,6 +114,7 @@ struct bic_ctx {
     DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
     DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_x, derived_list;
     bool derive_on = true;   // marginalise tables from counted supersets when the dataset is large
+    long long l2_window = 32ll << 20;   // bytes of dataset (all columns of one row slice) kept L2-resident; BIC_L2_WINDOW_MB overrides (tuning)
     Header *d_hdr = nullptr, *h_hdr = nullptr;
 
     // profiling
@@ -279,7 +281,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     na.all = all_tables ? 1 : 0;
     const long long target = (long long)c->sm_count * 8;
     const long long smax = std::max<long long>(1, c->N / 65536);
-    const long long L2_WINDOW = 32ll << 20;
+    const long long L2_WINDOW = c->l2_window;
     const long long s_l2 = ((long long)c->n * c->N + L2_WINDOW - 1) / L2_WINDOW;
     bool any_table = all_tables;
     for (int k = 0; k < NCLASS; ++k) {
@@ -581,6 +583,8 @@ int bic_create(bic_ctx **out, int device) {
         return BIC_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) ctx->l2_window = mb << 20; }
+    if (const char *e = getenv("BIC_NO_DERIVE")) ctx->derive_on = atoi(e) == 0;
     *out = ctx;
     return BIC_OK;
 }

@@ -317,8 +317,11 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     __syncthreads();
 
     const u32 cells = m.cells;
+    // slice boundaries on multiples of 8 vectors (128 bytes): a warp's 512-byte load then covers
+    // exactly 4 cache lines (ncu showed 5.2 data-pipe wavefronts per load with unaligned slices)
     const long long nvec = (a.N + 15) >> 4;
-    const long long v0 = nvec * slice / a.S, v1 = nvec * (slice + 1) / a.S;
+    const long long v0 = (nvec * slice / a.S) & ~7ll;
+    const long long v1 = (slice + 1 == a.S) ? nvec : ((nvec * (slice + 1) / a.S) & ~7ll);
     if (threadIdx.x == 0) {
         // replicas pay off only when the row loop dwarfs zeroing + summing R tables:
         // at least 16 rows per replicated counter
