@@ -344,7 +344,8 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         // mid-size tables (257..3072 cells) 112 KB x 2 CTAs or 192 KB x 1 CTA for replicas is
         // SLOWER (7.2 vs 5.8 us per family at 10 M rows): with ~224 KB of the SM carved out as
         // shared memory too little L1 is left to land the in-flight streaming loads.
-        const u32 cap[NCLASS] = {CLASS0_WORDS, CLASS1_CELLS, CLASS2_CELLS, 0};
+        static const u32 c0w = getenv("BIC_CLASS0_WORDS") ? (u32)atoi(getenv("BIC_CLASS0_WORDS")) : CLASS0_WORDS;   // tuning
+        const u32 cap[NCLASS] = {c0w, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
         if (k == 0) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32))));

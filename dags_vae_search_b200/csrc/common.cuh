@@ -20,7 +20,9 @@ constexpr int DERIVE_LEVELS = 32;          // families with fewer parents than t
 // memory (one privatised histogram per CTA), class 3 counts straight into HBM with L2 atomics.
 constexpr int NCLASS = 4;
 constexpr u32 CLASS0_CELLS = 2048;         //   8 KB of int32 -> many CTAs per SM
-constexpr u32 CLASS0_WORDS = 8192;         //  32 KB per class-0 CTA: room for lane replicas (count_kernels.cuh)
+constexpr u32 CLASS0_WORDS = 6144;         //  24 KB per class-0 CTA: room for lane replicas (count_kernels.cuh).  Swept 16..48 KB on
+                                           //  B200: 24 KB is best; at 48 KB (192 KB per SM) the kernel is 15 % slower because too
+                                           //  little L1 is left to land the in-flight streaming loads
 constexpr u32 CLASS1_CELLS = 12288;        //  48 KB
 constexpr u32 CLASS2_CELLS = 49152;        // 192 KB (one CTA per SM)
 
