@@ -97,6 +97,8 @@ struct bic_ctx {
 
     // dataset
     uint8_t *data = nullptr;
+    uint8_t *data2 = nullptr;    // 2-bit packed shadow copy (columns with <= 4 states), stride2 = stride / 4
+    long long stride2 = 0;
     long long N = 0, stride = 0, N_total = 0;
     int n = 0, W64 = 0, Wk = 0;
     int *d_card = nullptr;
@@ -306,6 +308,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
 
     CountArgs a;
     a.data = c->data; a.N = c->N; a.stride = c->stride; a.card = c->d_card; a.W64 = c->W64;
+    a.data2 = c->data2; a.stride2 = c->stride2;
     a.keys = keys; a.key_base = key_base;
     a.arena = c->arena.as<u32>();
     a.need = any_table ? c->need.as<u32>() : nullptr;
@@ -602,6 +605,7 @@ int bic_destroy(bic_ctx *c) {
                       &c->derived_list};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
+    if (c->data2) cudaFree(c->data2);
     if (c->d_card) cudaFree(c->d_card);
     if (c->d_hdr) cudaFree(c->d_hdr);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
@@ -644,8 +648,9 @@ int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int6
     cache_free(c);
     c->lookups = c->misses = 0;
     if (c->data) { cudaFree(c->data); c->data = nullptr; }
+    if (c->data2) { cudaFree(c->data2); c->data2 = nullptr; }
     if (c->d_card) { cudaFree(c->d_card); c->d_card = nullptr; }
-    long long pstride = (N + 127) / 128 * 128;   // every column 128-byte aligned; tail rows hold state 0
+    long long pstride = (N + 511) / 512 * 512;   // every column (and its 2-bit copy) 128-byte aligned; tail rows hold state 0
     CU(cudaMalloc(&c->data, (size_t)pstride * n));
     CU(cudaMalloc(&c->d_card, (size_t)n * sizeof(int)));
     CU(cudaMemsetAsync(c->data, 0, (size_t)pstride * n, c->stream));
@@ -665,6 +670,20 @@ int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int6
         cudaFree(c->data);
         c->data = nullptr;
         return fail(c, BIC_ERR_BAD_CODE, "dataset holds a state code >= its declared cardinality");
+    }
+    // 2-bit shadow copy, worth it only when rows are streamed from HBM/L2 many times
+    bool any_small = false;
+    for (int v = 0; v < n; ++v) any_small = any_small || card[v] <= 4;
+    long long pack_min = 1ll << 16;
+    if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack_min = atoll(e);   // tests force the packed path on small data
+    if (any_small && N >= pack_min && !getenv("BIC_NO_PACK2")) {
+        c->stride2 = pstride / 4;
+        CU(cudaMalloc(&c->data2, (size_t)c->stride2 * n));
+        CU(cudaMemsetAsync(c->data2, 0, (size_t)c->stride2 * n, c->stream));
+        dim3 g2((unsigned)std::min<long long>(2048, (pstride / 16 + 255) / 256), (unsigned)n);
+        k_pack2<<<g2, 256, 0, c->stream>>>(c->data, pstride, n, c->d_card, c->data2, c->stride2); LAUNCH(c);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
     }
     return BIC_OK;
 }

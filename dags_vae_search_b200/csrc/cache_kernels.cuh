@@ -465,4 +465,30 @@ __global__ void k_validate(const uint8_t *__restrict__ data, long long N, long l
     if (b) atomicOr(bad, 1u);
 }
 
+// ------------------------------------------------------------ 2-bit shadow copy of the dataset
+// Columns with at most 4 states also get a packed copy, 4 rows per byte (row p of a group of 16
+// in bits 2p..2p+1 of a 32-bit word).  The count kernel streams it instead of the uint8 column
+// when every column of a family qualifies: a quarter of the load traffic through the L1TEX data
+// pipe, which is what limits the kernel.  One thread packs 16 rows.
+__global__ void k_pack2(const uint8_t *__restrict__ data, long long stride, int n, const int *__restrict__ card,
+                        uint8_t *data2, long long stride2) {
+    int v = blockIdx.y;
+    if (card[v] > 4) return;
+    long long nvec = stride >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(data + (long long)v * stride);
+    u32 *dst = reinterpret_cast<u32 *>(data2 + (long long)v * stride2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        uint4 w = src[i];
+        const u32 ws[4] = {w.x, w.y, w.z, w.w};
+        u32 out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u32 x = ws[k];
+            u32 b = (x & 3u) | (((x >> 8) & 3u) << 2) | (((x >> 16) & 3u) << 4) | (((x >> 24) & 3u) << 6);
+            out |= b << (8 * k);
+        }
+        dst[i] = out;
+    }
+}
+
 }  // namespace bic

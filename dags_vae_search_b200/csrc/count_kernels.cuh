@@ -17,8 +17,10 @@ namespace bic {
 
 struct CountArgs {
     const uint8_t *data;     // [n][stride] uint8 state codes
+    const uint8_t *data2;    // [n][stride2] 2-bit packed copy of the columns with <= 4 states (nullable)
     long long N;             // rows on this GPU
     long long stride;
+    long long stride2;
     const int *card;
     int W64;
     const u64 *keys;         // family keys; job j uses keys + (key_base + j) * (W64 + 1)
@@ -41,6 +43,7 @@ struct CountArgs {
 struct FamMeta {
     int k, node, r;
     u32 q, cells;
+    int small;  // every column of the family has <= 4 states (2-bit packed copy usable)
     u32 R;      // lane replicas of the shared-memory table (power of two, <= 32)
     u32 mul;    // byte offset of a cell = cell * mul  (mul = 4 * R)
     int par[KMAX];
@@ -53,6 +56,7 @@ __device__ __forceinline__ void decode_family(const u64 *key, int W64, const int
     m.node = (int)key[0];
     m.r = card[m.node];
     int k = 0;
+    int small = m.r <= 4;
     u32 q = 1;
     for (int w = 0; w < W64; ++w) {
         u64 bits = key[1 + w];
@@ -65,6 +69,7 @@ __device__ __forceinline__ void decode_family(const u64 *key, int W64, const int
                 m.par[k] = p;
                 m.rad[k] = (u32)c;
                 q *= (u32)c;
+                small = small && c <= 4;
                 ++k;
             }
         }
@@ -72,6 +77,7 @@ __device__ __forceinline__ void decode_family(const u64 *key, int W64, const int
     m.k = k;
     m.q = q;
     m.cells = q * (u32)m.r;
+    m.small = small;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -216,6 +222,84 @@ __device__ __forceinline__ void count_rows_mode(const FamMeta &m, const uint8_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// 2-bit packed path (every column of the family has <= 4 states).  One 128-bit load now holds
+// 64 rows of a column, so the L1TEX data pipe moves a quarter of the bytes.  A 32-bit word (16
+// rows) is opened into 4 byte-lane registers with (W >> 2s) & 0x03030303: register s, byte lane
+// B = row 4B + s.  The mixed-radix index is built in byte lanes (4 rows per IMAD): the last
+// four columns (radices <= 4, so < 256 combinations) form the low group, the up to three
+// columns before them the high group; both are widened to 16-bit lanes with PRMT and combined
+// as hi * (P_low * mul) + lo * mul, which is the byte offset of the counter.
+__device__ __forceinline__ void unpack2(u32 W, u32 (&u)[4]) {
+    u[0] = W & 0x03030303u;
+    u[1] = (W >> 2) & 0x03030303u;
+    u[2] = (W >> 4) & 0x03030303u;
+    u[3] = (W >> 6) & 0x03030303u;
+}
+
+template <int K, bool MASKED>
+__device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 mul, u32 plow_mul,
+                                         u32 *hist, int lim) {
+    constexpr int C = K + 1;                  // columns, child last
+    constexpr int C1 = C > 4 ? C - 4 : 0;     // columns of the high group
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+        u32 hi[4], lo[4];
+#pragma unroll
+        for (int a = 0; a < C; ++a) {
+            const u32 W = wd == 0 ? w[a].x : wd == 1 ? w[a].y : wd == 2 ? w[a].z : w[a].w;
+            u32 u[4];
+            unpack2(W, u);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (a < C1) hi[s] = (a == 0) ? u[s] : hi[s] * rad[a] + u[s];
+                else lo[s] = (a == C1) ? u[s] : lo[s] * rad[a] + u[s];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            u32 t01 = __byte_perm(lo[s], 0u, 0x4140u) * mul;   // rows B = 0, 1 in 16-bit lanes
+            u32 t23 = __byte_perm(lo[s], 0u, 0x4342u) * mul;   // rows B = 2, 3
+            if (C1 > 0) {
+                t01 += __byte_perm(hi[s], 0u, 0x4140u) * plow_mul;
+                t23 += __byte_perm(hi[s], 0u, 0x4342u) * plow_mul;
+            }
+            const u32 off[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
+#pragma unroll
+            for (int B = 0; B < 4; ++B)
+                if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, off[B]);
+        }
+    }
+}
+
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
+                                              long long N, long long g0, long long g1, u32 *hist) {
+    constexpr int C = K + 1;
+    constexpr int C1 = C > 4 ? C - 4 : 0;
+    const uint8_t *cp[C];
+    u32 rad[C];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data2 + (long long)m.par[a] * stride2;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data2 + (long long)m.node * stride2;
+    rad[K] = (u32)m.r;
+    u32 plow = 1;
+#pragma unroll
+    for (int a = C1; a < C; ++a) plow *= rad[a];
+    const u32 mul = m.mul, plow_mul = plow * mul;
+    for (long long g = g0 + threadIdx.x; g < g1; g += THREADS) {
+        uint4 w[C];
+#pragma unroll
+        for (int a = 0; a < C; ++a) w[a] = ld_stream_v4(cp[a] + g * 16);
+        const long long row0 = g * 64;
+        if (row0 + 64 <= N) p2_group<K, false>(w, rad, mul, plow_mul, hist, 64);
+        else p2_group<K, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
+    }
+}
+
 // Any number of parents (k > 6): columns are walked one at a time.
 template <bool GLOBAL, int THREADS>
 __device__ __forceinline__ void count_rows_any(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
@@ -322,6 +406,10 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     const long long nvec = (a.N + 15) >> 4;
     const long long v0 = (nvec * slice / a.S) & ~7ll;
     const long long v1 = (slice + 1 == a.S) ? nvec : ((nvec * (slice + 1) / a.S) & ~7ll);
+    // the same slice in 64-row groups of the 2-bit packed copy
+    const long long ngrp = (a.N + 63) >> 6;
+    const long long g0 = (ngrp * slice / a.S) & ~7ll;
+    const long long g1 = (slice + 1 == a.S) ? ngrp : ((ngrp * (slice + 1) / a.S) & ~7ll);
     if (threadIdx.x == 0) {
         // replicas pay off only when the row loop dwarfs zeroing + summing R tables:
         // at least 16 rows per replicated counter
@@ -347,6 +435,21 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         __syncthreads();
     }
 
+    // packed path: all columns <= 4 states, index * mul fits 16-bit lanes.  The choice must not
+    // depend on the slice (the two paths cut the rows into slices differently), hence no R here:
+    // R > 1 implies cells * R <= cap_words <= 12288.
+    const bool packed = !GLOBAL && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
+    if (packed) {
+        switch (m.k) {
+            case 0: count_rows_p2<0, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 1: count_rows_p2<1, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 2: count_rows_p2<2, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 3: count_rows_p2<3, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 4: count_rows_p2<4, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 5: count_rows_p2<5, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            default: count_rows_p2<6, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+        }
+    } else
     switch (m.k) {
         case 0: count_rows_mode<0, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
         case 1: count_rows_mode<1, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;

@@ -395,3 +395,39 @@ def test_derived_families_match_counted_ones():
         b = s.score_adjacency(dags, no_cache=True)
         assert np.array_equal(a, b)
         assert_scores(a[:40], C.score_dags_adj(codes, card, dags[:40]))
+
+
+# ------------------------------------------------- 2-bit packed shadow copy of the dataset
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 511, 513, 4097, 70001])
+def test_packed_path_ragged_rows(N, monkeypatch):
+    """Columns with <= 4 states are also held 4 rows per byte and streamed from there.  Force
+    that path on small, ragged row counts (tail masking of the 64-row groups) and on families
+    with 1..7 columns (single- and two-group index arithmetic); mixed with a 5-state column
+    that must fall back to the uint8 path."""
+    monkeypatch.setenv("BIC_PACK2_MIN_ROWS", "1")
+    rng = np.random.default_rng(N)
+    card = np.array([2, 3, 4, 4, 3, 2, 4, 5, 1, 3], dtype=np.int32)
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    fams = [(0, []), (1, [0]), (2, [0, 1]), (3, [0, 1, 2]), (4, [0, 1, 2, 3]), (5, [0, 1, 2, 3, 4]),
+            (6, [0, 1, 2, 3, 4, 5]), (9, [0, 1, 2, 3, 4, 5, 6]), (6, [1, 3, 7]), (7, [2, 3]), (3, [8, 9]),
+            (2, [3, 4, 6, 9]), (0, [1, 2, 3, 4, 5, 6, 9])]
+    with pkg.BicScorer(codes, card) as s:
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for (i, ps), t in zip(fams, tabs):
+            assert np.array_equal(t, O.family_counts(codes, card, i, ps)), (N, i, ps)
+        node, off, par = csr_of(fams)
+        assert_scores(s.score_families_csr(node, off, par, no_cache=True), C.score_families(codes, card, node, off, par))
+
+
+def test_packed_and_byte_paths_agree(monkeypatch):
+    N = 600_000
+    adj, card, cpts = synth.make_network(12, 18, 3, [2, 3, 4], seed=41)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(42))
+    dags = synth.er_candidates(12, 400, 11, 30, 6, seed=43)
+    with pkg.BicScorer(codes, card) as s:
+        packed = s.score_adjacency(dags, no_cache=True)
+    monkeypatch.setenv("BIC_NO_PACK2", "1")
+    with pkg.BicScorer(codes, card) as s:
+        plain = s.score_adjacency(dags, no_cache=True)
+    assert np.array_equal(packed, plain)
+    assert_scores(packed[:30], C.score_dags_adj(codes, card, dags[:30]))
