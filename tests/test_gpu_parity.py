@@ -431,3 +431,82 @@ def test_packed_and_byte_paths_agree(monkeypatch):
         plain = s.score_adjacency(dags, no_cache=True)
     assert np.array_equal(packed, plain)
     assert_scores(packed[:30], C.score_dags_adj(codes, card, dags[:30]))
+
+
+# ------------------------------------------------------- sub-batching, cache growth, misc API
+def test_large_batch_spans_sub_batches(asia, asia_scorer):
+    """600k DAGs x 8 nodes = 4.8 M instances > the 4 M-instance sub-batch: two passes through the
+    dedup / count / gather pipeline, host CSR offsets re-based per sub-batch."""
+    codes, card = asia
+    base = synth.er_candidates(8, 3000, 5, 14, None, seed=77)
+    reps = 200
+    adj = np.concatenate([base] * reps)
+    want = np.tile(C.score_dags_adj(codes, card, base), reps)
+    asia_scorer.cache_clear()
+    got = asia_scorer.score_adjacency(adj)
+    assert got.shape == (600000,)
+    assert_scores(got, want)
+    # CSR entry point over the same batch
+    b, c_, p = np.nonzero(adj.transpose(0, 2, 1))
+    counts = np.bincount(b * 8 + c_, minlength=adj.shape[0] * 8)
+    off = np.zeros(adj.shape[0] * 8 + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    got_csr = asia_scorer.score_csr(off, p.astype(np.int32), adj.shape[0])
+    assert np.array_equal(got_csr, got)
+    import torch
+    dev = asia_scorer.score_adjacency(torch.from_numpy(adj).cuda())
+    assert np.array_equal(dev.cpu().numpy(), got)
+
+
+def test_cache_growth_reserve_and_stats(sachs):
+    codes, card = sachs
+    with pkg.BicScorer(codes, card) as s:
+        st0 = s.cache_stats()
+        assert st0["families"] == 0
+        s.cache_reserve(200_000)
+        assert s.cache_stats()["capacity"] >= 200_000
+        fams = all_families(11, max_k=3)          # 11 * (1 + 10 + 45 + 120) = 1936 families
+        node, off, par = csr_of(fams)
+        a = s.score_families_csr(node, off, par)
+        st = s.cache_stats()
+        assert st["families"] == len(fams) and st["misses"] == len(fams) and st["lookups"] == len(fams)
+        b = s.score_families_csr(node, off, par)     # all hits
+        st = s.cache_stats()
+        assert st["misses"] == len(fams) and st["lookups"] == 2 * len(fams)
+        assert np.array_equal(a, b)
+        # growth by rehash keeps every cached family
+        dags = synth.er_candidates(11, 150_000, 10, 25, None, seed=5)
+        s.score_adjacency(dags)
+        assert np.array_equal(s.score_families_csr(node, off, par), a)
+        s.cache_clear()
+        assert s.cache_stats()["families"] == 0
+        assert np.array_equal(s.score_families_csr(node, off, par), a)
+
+
+def test_stream_profile_and_metric_switch(asia, asia_scorer):
+    import torch
+    codes, card = asia
+    adj = synth.er_candidates(8, 256, 7, 12, None, seed=3)
+    ref = asia_scorer.score_adjacency(adj, no_cache=True)
+    stream = torch.cuda.Stream()
+    asia_scorer.set_stream(stream.cuda_stream)
+    asia_scorer.profile_enable(True)
+    asia_scorer.profile_reset()
+    got = asia_scorer.score_adjacency(adj, no_cache=True)
+    prof = asia_scorer.profile()
+    asia_scorer.profile_enable(False)
+    asia_scorer.set_stream(None)
+    assert np.array_equal(got, ref)
+    assert prof["count_launches"] >= 1 and prof["kernel_launches"] > prof["count_launches"]
+    assert prof["families_counted"] + prof["families_derived"] == asia_scorer.cache_stats()["families"]
+    assert prof["count_ms"] > 0 and prof["alg_bytes"] > 0 and prof["rows_counted"] == prof["families_counted"] * 5000
+    # one cache serves every metric: penalties are applied at gather time
+    ll = asia_scorer.score_adjacency(adj, metric="loglik")
+    aic = asia_scorer.score_adjacency(adj, metric="aic")
+    misses = asia_scorer.cache_stats()["misses"]
+    bic = asia_scorer.score_adjacency(adj, metric="bic")
+    assert asia_scorer.cache_stats()["misses"] == misses
+    nparams = ll - aic
+    assert np.allclose(bic, ll - 0.5 * np.log(5000) * nparams, rtol=1e-13)
+    with pytest.raises(NotImplementedError):
+        asia_scorer.score_adjacency(adj, metric="bde")
