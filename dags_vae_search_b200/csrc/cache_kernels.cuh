@@ -331,11 +331,14 @@ __device__ __forceinline__ long long cache_find(const u64 *key, int Wk, const u3
     }
 }
 
-// Donor search.  Counts are additive over a parent's states, so the table of family (i, P) is
-// the table of (i, P + {x}) summed over x — no pass over the rows.  For every new family look
-// for a *new* family of the same node with exactly one more parent (its table exists in this
-// sub-batch); among several pick the cheapest (smallest cardinality of x, then smallest x),
-// which makes the choice — like the ids — independent of thread timing.
+// Donor search.  A count table is the joint contingency table of the family's variables
+// {node} + P; which of them is the child only fixes the axis order.  Counts are additive over a
+// variable's states, so the table of family (y, Q) is the table of ANY family whose variable set
+// is {y} + Q + {x}, summed over x and re-ordered — no pass over the rows.  For every new family
+// probe (read-only) for a *new* family (c, V - {c}) with V = {y} + Q + {x}, over all x and all
+// child designations c in V (its table exists in this sub-batch).  Among several donors pick the
+// cheapest (smallest cardinality of x, then smallest x, then smallest c), which makes the choice
+// — like the ids — independent of thread timing.
 __global__ void k_find_donor(const u64 *__restrict__ regkeys, int W64, long long base, const Header *hdr,
                              const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, int n,
                              int enable, int *donor, int *donor_x) {
@@ -345,26 +348,42 @@ __global__ void k_find_donor(const u64 *__restrict__ regkeys, int W64, long long
     donor_x[j] = -1;
     if (!enable) return;
     int Wk = W64 + 1;
-    u64 key[W64MAX + 1];
+    u64 vset[W64MAX];        // {y} + Q
+    u64 key[W64MAX + 1];     // candidate donor key
     const u64 *mine = regkeys + (base + j) * Wk;
+    int node = (int)mine[0];
     int pc = 0;
-    for (int w = 0; w < Wk; ++w) key[w] = mine[w];
-    for (int w = 1; w < Wk; ++w) pc += __popcll(key[w]);
+    for (int w = 0; w < W64; ++w) {
+        vset[w] = mine[1 + w];
+        pc += __popcll(vset[w]);
+    }
     if (pc >= DERIVE_LEVELS - 1) return;
-    int node = (int)key[0];
+    vset[node >> 6] |= 1ull << (node & 63);
     int best_card = 1 << 30;
     for (int x = 0; x < n; ++x) {
-        if (x == node || card[x] < 2 || card[x] >= best_card) continue;
-        u64 bit = 1ull << (x & 63);
-        if (key[1 + (x >> 6)] & bit) continue;
-        key[1 + (x >> 6)] |= bit;
-        long long id = cache_find(key, Wk, table, mask, regkeys);
-        key[1 + (x >> 6)] &= ~bit;
-        if (id >= base) {
-            best_card = card[x];
-            donor[j] = (int)(id - base);
-            donor_x[j] = x;
+        if (card[x] < 2 || card[x] >= best_card) continue;
+        if (vset[x >> 6] & (1ull << (x & 63))) continue;
+        vset[x >> 6] |= 1ull << (x & 63);
+        bool found = false;
+        for (int w = 0; w < W64 && !found; ++w) {
+            u64 bits = vset[w];
+            while (bits && !found) {
+                int b = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                int c = w * 64 + b;                     // child designation of the candidate donor
+                key[0] = (u64)c;
+                for (int v = 0; v < W64; ++v) key[1 + v] = vset[v];
+                key[1 + (c >> 6)] &= ~(1ull << (c & 63));
+                long long id = cache_find(key, Wk, table, mask, regkeys);
+                if (id >= base) {
+                    best_card = card[x];
+                    donor[j] = (int)(id - base);
+                    donor_x[j] = x;
+                    found = true;
+                }
+            }
         }
+        vset[x >> 6] &= ~(1ull << (x & 63));
     }
 }
 

@@ -506,29 +506,46 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     }
 }
 
-// Derived families: table(i, P)[j_hi, lo] = sum over the states of x of table(i, P + {x})
-// [(j_hi * r_x + x) * L + lo], L = product of the radices after x (parents > x, then the
-// child).  One CTA per derived family; levels (number of parents) run high to low so a donor that
-// is itself derived is complete.  Then the usual fp64 reduce.
+// Derived families.  The donor's table is the joint table over {y} + Q + {x} in the donor's own
+// axis order (its parents ascending, its child last).  Target cell t = (digits over Q ascending,
+// then y) maps to the donor offset sum_v digit_v * stride_donor(v); the x axis is summed out.
+// One CTA per derived family; levels (number of parents) run high to low so a donor that is
+// itself derived is complete.  Then the usual fp64 reduce.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__restrict__ derived_list, int level) {
-    __shared__ FamMeta m;
+    __shared__ FamMeta m, md;
     __shared__ double s_red[32];
-    __shared__ u32 s_L, s_rx;
+    __shared__ u32 s_stride[KMAX + 1];   // donor stride of own axis a (parents 0..k-1, child k)
+    __shared__ u32 s_xstride, s_rx;
     __shared__ int s_go;
     const int j = derived_list[blockIdx.x];
     if (threadIdx.x == 0) {
-        const u64 *key = a.keys + (a.key_base + j) * (long long)(a.W64 + 1);
+        const long long Wk = a.W64 + 1;
+        const u64 *key = a.keys + (a.key_base + j) * Wk;
         int pc = 0;
         for (int w = 0; w < a.W64; ++w) pc += __popcll(key[1 + w]);
         s_go = (pc == level);
         if (s_go) {
             decode_family(key, a.W64, a.card, m);
-            int x = a.donor_x[j];
-            u32 L = (u32)m.r;
-            for (int p = 0; p < m.k; ++p)
-                if (m.par[p] > x) L *= m.rad[p];
-            s_L = L;
+            decode_family(a.keys + (a.key_base + a.donor[j]) * Wk, a.W64, a.card, md);
+            const int x = a.donor_x[j];
+            // donor strides by variable: child 1, then its parents from last to first
+            u32 st = (u32)md.r;
+            u32 xs = 0;
+            for (int q = 0; q <= m.k; ++q) s_stride[q] = 0;
+            for (int q = 0; q <= m.k; ++q) {
+                int v = q < m.k ? m.par[q] : m.node;
+                if (v == md.node) s_stride[q] = 1;
+            }
+            if (x == md.node) xs = 1;
+            for (int p = md.k - 1; p >= 0; --p) {
+                int v = md.par[p];
+                if (v == x) xs = st;
+                for (int q = 0; q <= m.k; ++q)
+                    if ((q < m.k ? m.par[q] : m.node) == v) s_stride[q] = st;
+                st *= md.rad[p];
+            }
+            s_xstride = xs;
             s_rx = (u32)a.card[x];
         }
     }
@@ -536,12 +553,18 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
     if (!s_go) return;
     const u32 *dt = a.arena + a.table_off[a.donor[j]];
     u32 *mt = a.arena + a.table_off[j];
-    const u32 L = s_L, rx = s_rx, cells = m.cells;
+    const u32 xs = s_xstride, rx = s_rx, cells = m.cells;
+    const int k = m.k;
     for (u32 t = threadIdx.x; t < cells; t += THREADS) {
-        u32 hi = t / L, lo = t - hi * L;
-        const u32 *src = dt + (size_t)hi * rx * L + lo;
+        u32 rem = t / (u32)m.r;
+        size_t src = (size_t)(t - rem * (u32)m.r) * s_stride[k];
+        for (int q = k - 1; q >= 0; --q) {
+            u32 nx = rem / m.rad[q];
+            src += (size_t)(rem - nx * m.rad[q]) * s_stride[q];
+            rem = nx;
+        }
         u32 s = 0;
-        for (u32 xv = 0; xv < rx; ++xv) s += __ldcg(src + (size_t)xv * L);
+        for (u32 xv = 0; xv < rx; ++xv) s += __ldcg(dt + src + (size_t)xv * xs);
         mt[t] = s;
     }
     __threadfence();

@@ -374,13 +374,15 @@ def test_derived_families_match_counted_ones():
     codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(22))
     # nested parent sets of node 0 and 5 -> chains of donors, plus unrelated families
     fams = [(0, []), (0, [1]), (0, [1, 2]), (0, [1, 2, 3]), (0, [1, 2, 3, 4]), (0, [2, 3]), (0, [3]),
-            (5, [0, 8]), (5, [0, 6, 8]), (5, [0, 1, 6, 8]), (5, [8]), (7, [6]), (7, [2, 6]), (4, [0, 1, 2, 3, 5, 6])]
+            (5, [0, 8]), (5, [0, 6, 8]), (5, [0, 1, 6, 8]), (5, [8]), (7, [6]), (7, [2, 6]), (4, [0, 1, 2, 3, 5, 6]),
+            # donors with a different child: {2,4,6} is inside {1,2,4,6} = family (1, [2,4,6]); {3,8} inside (8, [2,3])
+            (1, [2, 4, 6]), (6, [2, 4]), (4, [2, 6]), (8, [2, 3]), (3, [8]), (2, [3]), (3, []), (8, [])]
     node, off, par = csr_of(fams)
     with pkg.BicScorer(codes, card) as s:
         s.profile_reset()
         derived = s.score_families_csr(node, off, par, no_cache=True)
         prof = s.profile()
-        assert prof["families_derived"] >= 6 and prof["families_counted"] + prof["families_derived"] == len(fams)
+        assert prof["families_derived"] >= 9 and prof["families_counted"] + prof["families_derived"] == len(fams)
         s.derive = False
         s.profile_reset()
         counted = s.score_families_csr(node, off, par, no_cache=True)
