@@ -317,7 +317,6 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.ll_out = ll_out; a.np_out = np_out;
     a.reduce = sharded ? 0 : 1;
     a.donor = with_donors ? c->donor.as<int>() : nullptr;
-    a.donor_x = with_donors ? c->donor_x.as<int>() : nullptr;
     u32 class_count[NCLASS];
     u64 class_alg[NCLASS];
     for (int k = 0; k < NCLASS; ++k) { class_count[k] = h.class_count[k]; class_alg[k] = h.alg_bytes[k]; }
@@ -411,11 +410,15 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
                                          c->rank.as<u32>(), c->reg_count, c->regkeys, c->table); LAUNCH(c);
     // new families: find superset donors (large datasets only), then describe / classify
     CU(c->donor.ensure((size_t)T * sizeof(int)));
-    CU(c->donor_x.ensure((size_t)T * sizeof(int)));
+    CU(c->donor_x.ensure((size_t)T * sizeof(u64)));      // best (cells, index) of the donor search
     CU(c->derived_list.ensure((size_t)T * sizeof(int)));
     const int derive = (c->derive_on && !no_derive && c->N >= (1ll << 20)) ? 1 : 0;
-    k_find_donor<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
-                                           c->d_card, c->n, derive, c->donor.as<int>(), c->donor_x.as<int>()); LAUNCH(c);
+    if (derive) {
+        CU(cudaMemsetAsync(c->donor_x.p, 0xff, (size_t)T * sizeof(u64), c->stream));
+        k_announce<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
+                                             c->d_card, c->donor_x.as<u64>()); LAUNCH(c);
+    }
+    k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_x.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c);
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
                                              c->donor.as<int>(), c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
                                              c->derived_list.as<int>()); LAUNCH(c);

@@ -334,57 +334,86 @@ __device__ __forceinline__ long long cache_find(const u64 *key, int Wk, const u3
 // Donor search.  A count table is the joint contingency table of the family's variables
 // {node} + P; which of them is the child only fixes the axis order.  Counts are additive over a
 // variable's states, so the table of family (y, Q) is the table of ANY family whose variable set
-// is {y} + Q + {x}, summed over x and re-ordered — no pass over the rows.  For every new family
-// probe (read-only) for a *new* family (c, V - {c}) with V = {y} + Q + {x}, over all x and all
-// child designations c in V (its table exists in this sub-batch).  Among several donors pick the
-// cheapest (smallest cardinality of x, then smallest x, then smallest c), which makes the choice
-// — like the ids — independent of thread timing.
-__global__ void k_find_donor(const u64 *__restrict__ regkeys, int W64, long long base, const Header *hdr,
-                             const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, int n,
-                             int enable, int *donor, int *donor_x) {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= hdr->f_new) return;
-    donor[j] = -1;
-    donor_x[j] = -1;
-    if (!enable) return;
+// contains {y} + Q, summed over the extra variables and re-ordered — no pass over the rows.
+// The search is inverted: every new family G announces itself as a donor to all proper
+// sub-variable-sets S of its own set V (every child designation c in S; read-only probes for
+// the key (c, S - {c})); a hit that is new in this sub-batch records G with atomicMin on
+// (joint cells of G, G's index), so the cheapest donor wins and the plan — like the ids — does
+// not depend on thread timing.  |V| = 7 costs 7 * 2^6 = 448 probes; sets of more than
+// ANNOUNCE_MAX_VARS variables only announce to subsets missing one or two variables.
+constexpr int ANNOUNCE_MAX_VARS = 9;
+
+__device__ __forceinline__ void announce_to(const u64 *sub, int W64, u64 pack, long long base, const u32 *__restrict__ table,
+                                            u32 mask, const u64 *__restrict__ regkeys, u64 *best) {
+    u64 key[W64MAX + 1];
     int Wk = W64 + 1;
-    u64 vset[W64MAX];        // {y} + Q
-    u64 key[W64MAX + 1];     // candidate donor key
-    const u64 *mine = regkeys + (base + j) * Wk;
-    int node = (int)mine[0];
-    int pc = 0;
     for (int w = 0; w < W64; ++w) {
-        vset[w] = mine[1 + w];
-        pc += __popcll(vset[w]);
+        u64 bits = sub[w];
+        while (bits) {
+            int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            int c = w * 64 + b;                       // child designation
+            key[0] = (u64)c;
+            for (int v = 0; v < W64; ++v) key[1 + v] = sub[v];
+            key[1 + w] &= ~(1ull << b);
+            long long id = cache_find(key, Wk, table, mask, regkeys);
+            if (id >= base) atomicMin(best + (id - base), pack);
+        }
     }
-    if (pc >= DERIVE_LEVELS - 1) return;
+}
+
+__global__ void k_announce(const u64 *__restrict__ regkeys, int W64, long long base, const Header *hdr,
+                           const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, u64 *best) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= hdr->f_new) return;
+    int Wk = W64 + 1;
+    const u64 *mine = regkeys + (base + g) * Wk;
+    u64 vset[W64MAX], sub[W64MAX];
+    int vars[DERIVE_LEVELS + 1];
+    int node = (int)mine[0];
+    int m = 0;
+    u64 cells = 1;
+    for (int w = 0; w < W64; ++w) vset[w] = mine[1 + w];
     vset[node >> 6] |= 1ull << (node & 63);
-    int best_card = 1 << 30;
-    for (int x = 0; x < n; ++x) {
-        if (card[x] < 2 || card[x] >= best_card) continue;
-        if (vset[x >> 6] & (1ull << (x & 63))) continue;
-        vset[x >> 6] |= 1ull << (x & 63);
-        bool found = false;
-        for (int w = 0; w < W64 && !found; ++w) {
-            u64 bits = vset[w];
-            while (bits && !found) {
-                int b = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                int c = w * 64 + b;                     // child designation of the candidate donor
-                key[0] = (u64)c;
-                for (int v = 0; v < W64; ++v) key[1 + v] = vset[v];
-                key[1 + (c >> 6)] &= ~(1ull << (c & 63));
-                long long id = cache_find(key, Wk, table, mask, regkeys);
-                if (id >= base) {
-                    best_card = card[x];
-                    donor[j] = (int)(id - base);
-                    donor_x[j] = x;
-                    found = true;
-                }
+    for (int w = 0; w < W64; ++w) {
+        u64 bits = vset[w];
+        while (bits) {
+            int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (m <= DERIVE_LEVELS) vars[m] = w * 64 + b;
+            ++m;
+            cells *= (u64)card[w * 64 + b];
+            if (cells > MAX_CELLS) return;            // this family errors out anyway
+        }
+    }
+    if (m < 2 || m > DERIVE_LEVELS) return;
+    const u64 pack = (cells << 32) | (u64)g;
+    if (m <= ANNOUNCE_MAX_VARS) {
+        for (u32 pick = 1; pick + 1 < (1u << m); ++pick) {   // every non-empty proper subset
+            for (int w = 0; w < W64; ++w) sub[w] = 0;
+            for (int i = 0; i < m; ++i)
+                if (pick >> i & 1u) sub[vars[i] >> 6] |= 1ull << (vars[i] & 63);
+            announce_to(sub, W64, pack, base, table, mask, regkeys, best);
+        }
+    } else {
+        for (int i = 0; i < m; ++i) {
+            for (int w = 0; w < W64; ++w) sub[w] = vset[w];
+            sub[vars[i] >> 6] &= ~(1ull << (vars[i] & 63));
+            announce_to(sub, W64, pack, base, table, mask, regkeys, best);
+            for (int i2 = i + 1; i2 < m && m > 2; ++i2) {
+                sub[vars[i2] >> 6] &= ~(1ull << (vars[i2] & 63));
+                announce_to(sub, W64, pack, base, table, mask, regkeys, best);
+                sub[vars[i2] >> 6] |= 1ull << (vars[i2] & 63);
             }
         }
-        vset[x >> 6] &= ~(1ull << (x & 63));
     }
+}
+
+__global__ void k_pick_donor(const u64 *__restrict__ best, const Header *hdr, int enable, int *donor) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hdr->f_new) return;
+    u64 b = best[j];
+    donor[j] = (enable && b != ~0ull) ? (int)(b & 0xffffffffull) : -1;
 }
 
 // Describe the new families: counted ones get a count job, derived ones go to the derive list.

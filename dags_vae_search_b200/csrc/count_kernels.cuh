@@ -37,7 +37,6 @@ struct CountArgs {
     double *np_out;          // [key_base + j]  (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
-    const int *donor_x;      // per job: the parent summed out of the donor
 };
 
 struct FamMeta {
@@ -506,17 +505,18 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     }
 }
 
-// Derived families.  The donor's table is the joint table over {y} + Q + {x} in the donor's own
-// axis order (its parents ascending, its child last).  Target cell t = (digits over Q ascending,
-// then y) maps to the donor offset sum_v digit_v * stride_donor(v); the x axis is summed out.
-// One CTA per derived family; levels (number of parents) run high to low so a donor that is
-// itself derived is complete.  Then the usual fp64 reduce.
+// Derived families.  The donor's table is the joint table over a superset of {y} + Q in the
+// donor's own axis order (its parents ascending, its child last).  Target cell t = (digits over
+// Q ascending, then y) maps to the donor offset sum_v digit_v * stride_donor(v); the donor's
+// extra axes are summed out.  One CTA per derived family; levels (number of parents) run high to
+// low so a donor that is itself derived is complete.  Then the usual fp64 reduce.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__restrict__ derived_list, int level) {
     __shared__ FamMeta m, md;
     __shared__ double s_red[32];
-    __shared__ u32 s_stride[KMAX + 1];   // donor stride of own axis a (parents 0..k-1, child k)
-    __shared__ u32 s_xstride, s_rx;
+    __shared__ u32 s_stride[KMAX + 1];   // donor stride of own axis q (parents 0..k-1, child k)
+    __shared__ u32 s_xstride[KMAX + 1], s_xrad[KMAX + 1];   // the donor's extra axes
+    __shared__ u32 s_nx, s_xcells;
     __shared__ int s_go;
     const int j = derived_list[blockIdx.x];
     if (threadIdx.x == 0) {
@@ -528,43 +528,53 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
         if (s_go) {
             decode_family(key, a.W64, a.card, m);
             decode_family(a.keys + (a.key_base + a.donor[j]) * Wk, a.W64, a.card, md);
-            const int x = a.donor_x[j];
-            // donor strides by variable: child 1, then its parents from last to first
-            u32 st = (u32)md.r;
-            u32 xs = 0;
             for (int q = 0; q <= m.k; ++q) s_stride[q] = 0;
-            for (int q = 0; q <= m.k; ++q) {
-                int v = q < m.k ? m.par[q] : m.node;
-                if (v == md.node) s_stride[q] = 1;
-            }
-            if (x == md.node) xs = 1;
-            for (int p = md.k - 1; p >= 0; --p) {
-                int v = md.par[p];
-                if (v == x) xs = st;
+            u32 nx = 0, xcells = 1;
+            // walk the donor's axes from the fastest (its child) to the slowest (first parent)
+            u32 st = 1;
+            for (int p = md.k; p >= 0; --p) {
+                int v = p == md.k ? md.node : md.par[p];
+                u32 rad = p == md.k ? (u32)md.r : md.rad[p];
+                bool own = false;
                 for (int q = 0; q <= m.k; ++q)
-                    if ((q < m.k ? m.par[q] : m.node) == v) s_stride[q] = st;
-                st *= md.rad[p];
+                    if ((q < m.k ? m.par[q] : m.node) == v) { s_stride[q] = st; own = true; }
+                if (!own && rad > 1) {
+                    s_xstride[nx] = st;
+                    s_xrad[nx] = rad;
+                    xcells *= rad;
+                    ++nx;
+                }
+                st *= rad;
             }
-            s_xstride = xs;
-            s_rx = (u32)a.card[x];
+            s_nx = nx;
+            s_xcells = xcells;
         }
     }
     __syncthreads();
     if (!s_go) return;
     const u32 *dt = a.arena + a.table_off[a.donor[j]];
     u32 *mt = a.arena + a.table_off[j];
-    const u32 xs = s_xstride, rx = s_rx, cells = m.cells;
+    const u32 nx = s_nx, xcells = s_xcells, cells = m.cells;
     const int k = m.k;
     for (u32 t = threadIdx.x; t < cells; t += THREADS) {
         u32 rem = t / (u32)m.r;
         size_t src = (size_t)(t - rem * (u32)m.r) * s_stride[k];
         for (int q = k - 1; q >= 0; --q) {
-            u32 nx = rem / m.rad[q];
-            src += (size_t)(rem - nx * m.rad[q]) * s_stride[q];
-            rem = nx;
+            u32 nxt = rem / m.rad[q];
+            src += (size_t)(rem - nxt * m.rad[q]) * s_stride[q];
+            rem = nxt;
         }
         u32 s = 0;
-        for (u32 xv = 0; xv < rx; ++xv) s += __ldcg(dt + src + (size_t)xv * xs);
+        for (u32 e = 0; e < xcells; ++e) {
+            u32 er = e;
+            size_t o = src;
+            for (u32 ax = 0; ax < nx; ++ax) {
+                u32 en = er / s_xrad[ax];
+                o += (size_t)(er - en * s_xrad[ax]) * s_xstride[ax];
+                er = en;
+            }
+            s += __ldcg(dt + o);
+        }
         mt[t] = s;
     }
     __threadfence();
