@@ -347,9 +347,12 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         // SLOWER (7.2 vs 5.8 us per family at 10 M rows): with ~224 KB of the SM carved out as
         // shared memory too little L1 is left to land the in-flight streaming loads.
         static const u32 c0w = getenv("BIC_CLASS0_WORDS") ? (u32)atoi(getenv("BIC_CLASS0_WORDS")) : CLASS0_WORDS;   // tuning
+        static const int c0t = getenv("BIC_CLASS0_THREADS") ? atoi(getenv("BIC_CLASS0_THREADS")) : 256;              // tuning
         const u32 cap[NCLASS] = {c0w, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
-        if (k == 0) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
+        if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
+        if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
+        if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32))));
         if (k == 2) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 3) TRY((launch_count<256, true>(c, a, items, 0)));

@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         u32 R = 1;
         const long long rows_here = (v1 - v0) * 16;
         if (!GLOBAL)
-            while (R < 32 && cells * (R * 2) <= a.cap_words && cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) &&
-                   (long long)cells * (R * 2) * 16 <= rows_here)
+            while (R < 32 && cells * (R * 2) <= a.cap_words && cells * (R * 2) <= 16383u &&   // 16-bit lane offsets
+                   cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) && (long long)cells * (R * 2) * 16 <= rows_here)
                 R *= 2;
         // measured (ncu source counters, tools/microbench2): R = 32 -> 1.00 wavefront per warp
         // atomic, 16 -> 2.0, none -> ~2.6, but 8 -> 2.8 and 4 -> 3.3 because interleaving then
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
 
     // packed path: all columns <= 4 states, index * mul fits 16-bit lanes.  The choice must not
     // depend on the slice (the two paths cut the rows into slices differently), hence no R here:
-    // R > 1 implies cells * R <= cap_words <= 12288.
+    // R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
         switch (m.k) {
