@@ -114,9 +114,26 @@ struct bic_ctx {
 
     // per-sub-batch workspace
     DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
-    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_x, derived_list;
-    bool derive_on = true;   // marginalise tables from counted supersets when the dataset is large
-    long long l2_window = 32ll << 20;   // bytes of dataset (all columns of one row slice) kept L2-resident; BIC_L2_WINDOW_MB overrides (tuning)
+    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_best, derived_list;
+    // Tuning knobs.  Defaults are the values swept on B200; the BIC_*
+    // environment variables exist for those sweeps and for tests, not as a supported interface.
+    struct Tuning {
+        bool derive = true;                    // BIC_NO_DERIVE=1: count every family from the rows
+        bool pack2 = true;                     // BIC_NO_PACK2=1: no 2-bit shadow copy
+        long long pack2_min_rows = 1ll << 20;  // BIC_PACK2_MIN_ROWS
+        long long derive_min_rows = 1ll << 20;
+        long long l2_window = 32ll << 20;      // BIC_L2_WINDOW_MB: dataset bytes of one row slice kept L2-resident
+        u32 class0_words = CLASS0_WORDS;       // BIC_CLASS0_WORDS: shared-memory words of a class-0 CTA
+        int class0_threads = 256;              // BIC_CLASS0_THREADS: 256, 512 or 1024
+        void from_env() {
+            if (const char *e = getenv("BIC_NO_DERIVE")) derive = atoi(e) == 0;
+            if (const char *e = getenv("BIC_NO_PACK2")) pack2 = atoi(e) == 0;
+            if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
+            if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
+            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
+            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) class0_threads = t; }
+        }
+    } tune;
     Header *d_hdr = nullptr, *h_hdr = nullptr;
 
     // profiling
@@ -183,15 +200,27 @@ void cache_free(bic_ctx *c) {
 int cache_ensure(bic_ctx *c, long long extra) {
     long long want = c->reg_count + extra;
     if (c->table && want <= c->reg_cap) return BIC_OK;
+    // cudaMalloc / cudaFree take anywhere from 1 ms to hundreds of ms here (measured), so growth must
+    // be rare: start at 2^20 families (40 MB) and leave 2x headroom over what is needed now
+    want = std::max<long long>(2 * want, 1ll << 20);
     u64 cap = 1ull << 16;
     while ((long long)(cap / 2) < want) cap <<= 1;
-    if (cap > (1ull << 30)) return fail(c, BIC_ERR_OOM, "family cache would exceed 2^30 slots; call bic_cache_clear()");
+    if (cap > (1ull << 30)) {
+        cap = 1ull << 30;
+        if ((long long)(cap / 2) < c->reg_count + extra)
+            return fail(c, BIC_ERR_OOM, "family cache would exceed 2^30 slots; call bic_cache_clear()");
+    }
     long long rcap = (long long)(cap / 2);
     u32 *ntable = nullptr; u64 *nkeys = nullptr; double *nll = nullptr, *nnp = nullptr;
-    CU(cudaMalloc(&ntable, cap * sizeof(u32)));
-    CU(cudaMalloc(&nkeys, (size_t)rcap * c->Wk * sizeof(u64)));
-    CU(cudaMalloc(&nll, (size_t)rcap * sizeof(double)));
-    CU(cudaMalloc(&nnp, (size_t)rcap * sizeof(double)));
+    if (cudaMalloc(&ntable, cap * sizeof(u32)) != cudaSuccess || cudaMalloc(&nkeys, (size_t)rcap * c->Wk * sizeof(u64)) != cudaSuccess ||
+        cudaMalloc(&nll, (size_t)rcap * sizeof(double)) != cudaSuccess || cudaMalloc(&nnp, (size_t)rcap * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        if (ntable) cudaFree(ntable);
+        if (nkeys) cudaFree(nkeys);
+        if (nll) cudaFree(nll);
+        if (nnp) cudaFree(nnp);
+        return fail(c, BIC_ERR_OOM, "device allocation for the family cache failed");
+    }
     CU(cudaMemsetAsync(ntable, 0, cap * sizeof(u32), c->stream));
     if (c->reg_count) {
         CU(cudaMemcpyAsync(nkeys, c->regkeys, (size_t)c->reg_count * c->Wk * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
@@ -283,7 +312,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     na.all = all_tables ? 1 : 0;
     const long long target = (long long)c->sm_count * 8;
     const long long smax = std::max<long long>(1, c->N / 65536);
-    const long long L2_WINDOW = c->l2_window;
+    const long long L2_WINDOW = c->tune.l2_window;
     const long long s_l2 = ((long long)c->n * c->N + L2_WINDOW - 1) / L2_WINDOW;
     bool any_table = all_tables;
     for (int k = 0; k < NCLASS; ++k) {
@@ -346,9 +375,8 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         // mid-size tables (257..3072 cells) 112 KB x 2 CTAs or 192 KB x 1 CTA for replicas is
         // SLOWER (7.2 vs 5.8 us per family at 10 M rows): with ~224 KB of the SM carved out as
         // shared memory too little L1 is left to land the in-flight streaming loads.
-        static const u32 c0w = getenv("BIC_CLASS0_WORDS") ? (u32)atoi(getenv("BIC_CLASS0_WORDS")) : CLASS0_WORDS;   // tuning
-        static const int c0t = getenv("BIC_CLASS0_THREADS") ? atoi(getenv("BIC_CLASS0_THREADS")) : 256;              // tuning
-        const u32 cap[NCLASS] = {c0w, CLASS1_CELLS, CLASS2_CELLS, 0};
+        const int c0t = c->tune.class0_threads;
+        const u32 cap[NCLASS] = {c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
@@ -413,15 +441,15 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
                                          c->rank.as<u32>(), c->reg_count, c->regkeys, c->table); LAUNCH(c);
     // new families: find superset donors (large datasets only), then describe / classify
     CU(c->donor.ensure((size_t)T * sizeof(int)));
-    CU(c->donor_x.ensure((size_t)T * sizeof(u64)));      // best (cells, index) of the donor search
+    CU(c->donor_best.ensure((size_t)T * sizeof(u64)));   // (joint cells, index) of the cheapest donor announced so far
     CU(c->derived_list.ensure((size_t)T * sizeof(int)));
-    const int derive = (c->derive_on && !no_derive && c->N >= (1ll << 20)) ? 1 : 0;
+    const int derive = (c->tune.derive && !no_derive && c->N >= c->tune.derive_min_rows) ? 1 : 0;
     if (derive) {
-        CU(cudaMemsetAsync(c->donor_x.p, 0xff, (size_t)T * sizeof(u64), c->stream));
+        CU(cudaMemsetAsync(c->donor_best.p, 0xff, (size_t)T * sizeof(u64), c->stream));
         k_announce<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
-                                             c->d_card, c->donor_x.as<u64>()); LAUNCH(c);
+                                             c->d_card, c->donor_best.as<u64>()); LAUNCH(c);
     }
-    k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_x.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c);
+    k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c);
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
                                              c->donor.as<int>(), c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
                                              c->derived_list.as<int>()); LAUNCH(c);
@@ -593,8 +621,7 @@ int bic_create(bic_ctx **out, int device) {
         return BIC_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) ctx->l2_window = mb << 20; }
-    if (const char *e = getenv("BIC_NO_DERIVE")) ctx->derive_on = atoi(e) == 0;
+    ctx->tune.from_env();
     *out = ctx;
     return BIC_OK;
 }
@@ -607,7 +634,7 @@ int bic_destroy(bic_ctx *c) {
     cache_free(c);
     DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
                       &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
-                      &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_x,
+                      &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_best,
                       &c->derived_list};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
@@ -675,6 +702,8 @@ int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int6
     if (c->h_hdr->err) {
         cudaFree(c->data);
         c->data = nullptr;
+        c->N = 0;
+        c->n = 0;
         return fail(c, BIC_ERR_BAD_CODE, "dataset holds a state code >= its declared cardinality");
     }
     // 2-bit shadow copy, worth it only when rows are streamed from HBM/L2 many times
@@ -682,9 +711,8 @@ int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int6
     for (int v = 0; v < n; ++v) any_small = any_small || card[v] <= 4;
     // measured: at 100 k rows the packed path is 1.7x SLOWER (a thread runs only ~6 iterations of a
     // long unrolled body; per-item overhead and instruction fetch dominate), at 10 M rows 1.4x faster
-    long long pack_min = 1ll << 20;
-    if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack_min = atoll(e);   // tests force the packed path on small data
-    if (any_small && N >= pack_min && !getenv("BIC_NO_PACK2")) {
+    c->tune.from_env();   // tests switch the packed path per dataset
+    if (any_small && c->tune.pack2 && N >= c->tune.pack2_min_rows) {
         c->stride2 = pstride / 4;
         CU(cudaMalloc(&c->data2, (size_t)c->stride2 * n));
         CU(cudaMemsetAsync(c->data2, 0, (size_t)c->stride2 * n, c->stream));

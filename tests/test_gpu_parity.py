@@ -465,8 +465,8 @@ def test_cache_growth_reserve_and_stats(sachs):
     with pkg.BicScorer(codes, card) as s:
         st0 = s.cache_stats()
         assert st0["families"] == 0
-        s.cache_reserve(200_000)
-        assert s.cache_stats()["capacity"] >= 200_000
+        s.cache_reserve(3_000_000)                 # beyond the 2^20-family initial size: grows
+        assert s.cache_stats()["capacity"] >= 3_000_000
         fams = all_families(11, max_k=3)          # 11 * (1 + 10 + 45 + 120) = 1936 families
         node, off, par = csr_of(fams)
         a = s.score_families_csr(node, off, par)
