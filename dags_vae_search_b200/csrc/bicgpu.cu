@@ -94,6 +94,7 @@ struct bic_ctx {
     std::mutex mu;
     std::string err;
     int sm_count = 148;
+    size_t attr_smem[6] = {0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
 
     // dataset
     uint8_t *data = nullptr;
@@ -262,10 +263,12 @@ int header_fetch(bic_ctx *c) {
     return BIC_OK;
 }
 
+// Dynamic shared memory above 48 KB needs a per-device opt-in on the kernel; the largest size set
+// so far is remembered per context (= per device) and per template instance.
 template <int THREADS, bool GLOBAL>
 int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
-    static size_t attr_smem = 40 * 1024;   // per template instance; static + dynamic over 48 KB needs the opt-in
-    if (smem > attr_smem) {
+    size_t &attr_smem = c->attr_smem[(THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
+    if (smem > 40 * 1024 && smem > attr_smem) {   // static + dynamic over 48 KB needs the opt-in
         CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }

@@ -66,3 +66,45 @@ def test_row_sharded_with_derived_families_world1():
         sharded = s.score_adjacency(dags, no_cache=True)
         assert s.profile()["families_derived"] > 0
         assert np.array_equal(sharded, plain)
+
+
+def test_two_contexts_from_two_threads(asia, sachs):
+    """Contexts are independent; calls on different contexts may overlap (ctypes drops the GIL)."""
+    import threading
+    a_adj = synth.er_candidates(8, 4000, 5, 14, None, seed=1)
+    s_adj = synth.er_candidates(11, 4000, 8, 25, None, seed=2)
+    with pkg.BicScorer(*asia) as sa, pkg.BicScorer(*sachs) as ss:
+        want_a = sa.score_adjacency(a_adj, no_cache=True)
+        want_s = ss.score_adjacency(s_adj, no_cache=True)
+        got = {}
+
+        def work(name, scorer, adj):
+            for _ in range(5):
+                got[name] = scorer.score_adjacency(adj, no_cache=True)
+
+        threads = [threading.Thread(target=work, args=("a", sa, a_adj)), threading.Thread(target=work, args=("s", ss, s_adj))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert np.array_equal(got["a"], want_a) and np.array_equal(got["s"], want_s)
+
+
+def test_two_devices_in_one_process(sachs):
+    """The >48 KB shared-memory opt-in of the count kernels is per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    codes, card = sachs
+    fams_nodes = [0, 1, 2]
+    fams_parents = [[1, 2, 3, 4, 5, 6, 7, 8], [0, 2, 3, 4, 5, 6, 7], [3, 4]]      # 19683 / 6561 / 27 cells
+    with pkg.BicScorer(codes, card, device=0) as s0, pkg.BicScorer(codes, card, device=1) as s1:
+        a = s0.score_families(fams_nodes, fams_parents)
+        b = s1.score_families(fams_nodes, fams_parents)
+        assert np.array_equal(a, b)
+        for i, ps, v in zip(fams_nodes, fams_parents, a):
+            assert v == pytest.approx(C.score_families(codes, card, *_csr1(i, ps))[0], rel=1e-9)
+
+
+def _csr1(i, ps):
+    return np.array([i], dtype=np.int32), np.array([0, len(ps)], dtype=np.int64), np.array(ps, dtype=np.int32)
