@@ -94,7 +94,7 @@ struct bic_ctx {
     std::mutex mu;
     std::string err;
     int sm_count = 148;
-    size_t attr_smem[6] = {0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
+    size_t attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
 
     // dataset
     uint8_t *data = nullptr;
@@ -132,7 +132,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
             if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
             if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
-            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) class0_threads = t; }
+            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) class0_threads = t; }
         }
     } tune;
     Header *d_hdr = nullptr, *h_hdr = nullptr;
@@ -267,7 +267,7 @@ int header_fetch(bic_ctx *c) {
 // so far is remembered per context (= per device) and per template instance.
 template <int THREADS, bool GLOBAL>
 int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
-    size_t &attr_smem = c->attr_smem[(THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
+    size_t &attr_smem = c->attr_smem[(THREADS == 128 ? 6 : THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
     if (smem > 40 * 1024 && smem > attr_smem) {   // static + dynamic over 48 KB needs the opt-in
         CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
@@ -381,6 +381,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         const int c0t = c->tune.class0_threads;
         const u32 cap[NCLASS] = {c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
+        if (k == 0 && c0t == 128) TRY((launch_count<128, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));

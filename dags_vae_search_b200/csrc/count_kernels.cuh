@@ -353,23 +353,14 @@ __device__ __forceinline__ void compact_replicas(u32 *hist, u32 cells, u32 R) {
 // therefore bit-identical for every kernel class, slice count and for the row-sharded path.
 constexpr int RED_LANES = 256;
 
-__device__ __forceinline__ double block_sum(double v, double *sh) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && threadIdx.x < RED_LANES) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    if (threadIdx.x == 0)
-        for (int w = 0; w < RED_LANES / 32; ++w) t += sh[w];
-    return t;
-}
-
-// k3: sum_{j,x: c>0} c * ln(c / N_ij).
+// k3: sum_{j,x: c>0} c * ln(c / N_ij).  Virtual lane v (0..255) owns parent configurations v,
+// v+256, ...; a block of fewer than 256 threads runs several virtual lanes per thread (a warp
+// always holds 32 consecutive virtual lanes), so the bits do not depend on the block size.
 template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh) {
-    double acc = 0.0;
-    if (threadIdx.x < RED_LANES) {
-        for (u32 j = threadIdx.x; j < q; j += RED_LANES) {
+    for (u32 vl = threadIdx.x; vl < RED_LANES; vl += blockDim.x) {
+        double acc = 0.0;
+        for (u32 j = vl; j < q; j += RED_LANES) {
             const u32 *row = tab + (size_t)j * r;
             u32 nij = 0;
             for (int x = 0; x < r; ++x) nij += FROM_GLOBAL ? __ldcg(row + x) : row[x];
@@ -381,8 +372,15 @@ __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, do
                 }
             }
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if ((vl & 31) == 0) sh[vl >> 5] = acc;
     }
-    return block_sum(acc, sh);
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < RED_LANES / 32; ++w) t += sh[w];
+    return t;
 }
 
 template <int THREADS, bool GLOBAL>
