@@ -18,7 +18,7 @@ FLAG_DEVICE_PTRS = 1
 FLAG_NO_CYCLE_CHECK = 2
 FLAG_NO_CACHE = 4
 FLAG_NO_DERIVE = 8
-METRICS = {"bic": 0, "loglik": 1, "aic": 2}
+METRICS = {"bic": 0, "loglik": 1, "aic": 2, "bde": 3, "k2": 4}
 
 STATUS_NAMES = {
     0: "BIC_OK", -1: "BIC_ERR_CUDA", -2: "BIC_ERR_ARG", -3: "BIC_ERR_NO_DATASET",
@@ -28,7 +28,7 @@ STATUS_NAMES = {
 
 # every symbol include/bicgpu.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_sync",
+    "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_sync", "bic_set_iss",
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
     "bic_cache_stats", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
     L.bic_last_error.restype = ctypes.c_char_p
     L.bic_set_stream.argtypes = [vp, vp]
     L.bic_sync.argtypes = [vp]
+    L.bic_set_iss.argtypes = [vp, ctypes.c_double]
     L.bic_set_dataset.argtypes = [vp, vp, i64, i32, i64, vp, ctypes.c_int]
     L.bic_count_families.argtypes = [vp, vp, vp, vp, i64, vp, vp, ctypes.c_int]
     L.bic_score_families.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.c_int]

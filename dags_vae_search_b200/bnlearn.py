@@ -34,8 +34,8 @@ class BNLearnWrapper:
         self.score_script_filename = score_script_filename   # kept for signature parity; unused
 
         if metric_name not in nat.METRICS:
-            # the reference forwards any bnlearn type= string (bnlearn_score.R:38); only the
-            # decomposable count-based ones are implemented here
+            # the reference forwards any bnlearn type= string (bnlearn_score.R:38); the decomposable
+            # count-based ones are implemented here: bic, loglik, aic, bde (BDeu, iss = 1), k2
             raise NotImplementedError(f"metric {metric_name!r}: only {sorted(nat.METRICS)} are implemented")
         codes, card, names = load_dataset(dataset_name)
         self.vertex_mapping = {i: label for i, label in enumerate(names)}   # bnlearn.py:23

@@ -112,6 +112,8 @@ struct bic_ctx {
     double *reg_ll = nullptr, *reg_np = nullptr;
     long long reg_cap = 0, reg_count = 0;
     long long lookups = 0, misses = 0;
+    int cache_mode = 0;      // what reg_ll holds: 0 log-likelihood (+ reg_np), 1 BDeu terms for `iss`, 2 K2 terms
+    double iss = 1.0;
 
     // per-sub-batch workspace
     DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
@@ -349,6 +351,8 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.ll_out = ll_out; a.np_out = np_out;
     a.reduce = sharded ? 0 : 1;
     a.donor = with_donors ? c->donor.as<int>() : nullptr;
+    a.bd_mode = c->cache_mode;
+    a.iss = c->iss;
     u32 class_count[NCLASS];
     u64 class_alg[NCLASS];
     for (int k = 0; k < NCLASS; ++k) { class_count[k] = h.class_count[k]; class_alg[k] = h.alg_bytes[k]; }
@@ -502,9 +506,16 @@ int stage_in(bic_ctx *c, const T *src, size_t count, int flags, DevBuf &buf, con
 
 int begin_call(bic_ctx *c, int metric, bool need_metric) {
     if (!c->data) return fail(c, BIC_ERR_NO_DATASET, "no dataset: call bic_set_dataset first");
-    if (need_metric && (metric < BIC_METRIC_BIC || metric > BIC_METRIC_AIC)) return fail(c, BIC_ERR_ARG, "unknown metric");
+    if (need_metric && (metric < BIC_METRIC_BIC || metric > BIC_METRIC_K2)) return fail(c, BIC_ERR_ARG, "unknown metric");
     CU(cudaSetDevice(c->device));
     TRY(refresh_ntotal(c));
+    if (need_metric) {   // the cache holds one kind of family term at a time
+        int mode = metric == BIC_METRIC_BDE ? 1 : metric == BIC_METRIC_K2 ? 2 : 0;
+        if (mode != c->cache_mode) {
+            TRY(cache_clear(c));
+            c->cache_mode = mode;
+        }
+    }
     return BIC_OK;
 }
 
@@ -658,6 +669,16 @@ int bic_set_stream(bic_ctx *c, void *cuda_stream) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return BIC_OK;
+}
+
+int bic_set_iss(bic_ctx *c, double iss) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!(iss > 0.0)) return fail(c, BIC_ERR_ARG, "iss must be positive");
+    CU(cudaSetDevice(c->device));
+    if (iss != c->iss && c->cache_mode == 1) TRY(cache_clear(c));
+    c->iss = iss;
     return BIC_OK;
 }
 

@@ -37,6 +37,8 @@ struct CountArgs {
     double *np_out;          // [key_base + j]  (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
+    int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
+    double iss;
 };
 
 struct FamMeta {
@@ -383,6 +385,43 @@ __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, do
     return t;
 }
 
+// Bayesian-Dirichlet family term (bnlearn "bde" = BDeu, "k2") on the same counts, same lane order:
+// sum_j [ lgamma(a_ij) - lgamma(a_ij + N_ij) + sum_x ( lgamma(a_ijk + c) - lgamma(a_ijk) ) ].
+template <bool FROM_GLOBAL>
+__device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double a_ij, double a_ijk, double *sh) {
+    const double lg_ij = lgamma(a_ij), lg_ijk = lgamma(a_ijk);
+    for (u32 vl = threadIdx.x; vl < RED_LANES; vl += blockDim.x) {
+        double acc = 0.0;
+        for (u32 j = vl; j < q; j += RED_LANES) {
+            const u32 *row = tab + (size_t)j * r;
+            u32 nij = 0;
+            double s = 0.0;
+            for (int x = 0; x < r; ++x) {
+                u32 c = FROM_GLOBAL ? __ldcg(row + x) : row[x];
+                nij += c;
+                if (c) s += lgamma(a_ijk + (double)c) - lg_ijk;
+            }
+            if (nij) acc += (lg_ij - lgamma(a_ij + (double)nij)) + s;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if ((vl & 31) == 0) sh[vl >> 5] = acc;
+    }
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < RED_LANES / 32; ++w) t += sh[w];
+    return t;
+}
+
+// The cached family term: log-likelihood (penalty applied at gather time) or a BD score.
+template <bool FROM_GLOBAL>
+__device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab, const FamMeta &m, double *sh) {
+    if (a.bd_mode == 0) return family_loglik<FROM_GLOBAL>(tab, m.q, m.r, sh);
+    double a_ijk = a.bd_mode == 1 ? a.iss / ((double)m.q * (double)m.r) : 1.0;
+    return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh);
+}
+
 template <int THREADS, bool GLOBAL>
 __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     extern __shared__ u32 s_hist[];
@@ -470,7 +509,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
 
     double ll;
     if (!GLOBAL && a.S == 1) {
-        ll = family_loglik<false>(s_hist, m.q, m.r, s_red);
+        ll = family_term<false>(a, s_hist, m, s_red);
     } else {
         __threadfence();
         __syncthreads();
@@ -478,11 +517,11 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        ll = family_loglik<true>(tab, m.q, m.r, s_red);
+        ll = family_term<true>(a, tab, m, s_red);
     }
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
-        a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
+        a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
     }
 }
 
@@ -496,10 +535,10 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     if (a.donor && a.donor[j] >= 0) return;   // derived families are reduced by k_derive
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
-    double ll = family_loglik<true>(a.arena + a.table_off[j], m.q, m.r, s_red);
+    double ll = family_term<true>(a, a.arena + a.table_off[j], m, s_red);
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
-        a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
+        a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
     }
 }
 
@@ -577,10 +616,10 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
     }
     __threadfence();
     __syncthreads();
-    double ll = family_loglik<true>(mt, m.q, m.r, s_red);
+    double ll = family_term<true>(a, mt, m, s_red);
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
-        a.np_out[a.key_base + j] = (double)(m.r - 1) * (double)m.q;
+        a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
     }
 }
 

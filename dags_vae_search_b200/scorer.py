@@ -34,9 +34,9 @@ def _family_csr(nodes: Sequence[int], parent_lists: Sequence[Iterable[int]]):
 
 
 class BicScorer:
-    """Decomposable discrete BN scores (bic / aic / loglik) of DAG batches on one B200."""
+    """Decomposable discrete BN scores (bic / aic / loglik / bde / k2) of DAG batches on one B200."""
 
-    def __init__(self, codes, card, device: int = 0, metric: str = "bic"):
+    def __init__(self, codes, card, device: int = 0, metric: str = "bic", iss: float = 1.0):
         if metric not in nat.METRICS:
             raise NotImplementedError(f"metric {metric!r}: only {sorted(nat.METRICS)} are implemented")
         self._lib = nat.lib()
@@ -49,6 +49,12 @@ class BicScorer:
             self._ctx = ctypes.c_void_p()
             raise nat.BicError(rc, msg.decode() if msg else "")
         self.set_dataset(codes, card)
+        if iss != 1.0:
+            self.set_iss(iss)
+
+    def set_iss(self, iss: float) -> None:
+        """Imaginary sample size of the ``bde`` (BDeu) metric, bnlearn's ``iss`` (default 1)."""
+        self._check(self._lib.bic_set_iss(self._ctx, float(iss)))
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:

@@ -17,7 +17,9 @@
  *   - count table of family (node i, parents P sorted ascending, first most significant):
  *     cell = j * r_i + x_i,  j = ((x_p1 * r_p2 + x_p2) * r_p3 + ...), int32 counters;
  *   - score = sum_i [ sum_{jk: N_ijk>0} N_ijk ln(N_ijk / N_ij)  -  pen * (r_i - 1) * q_i ],
- *     pen = 0.5 ln N (bic), 1 (aic), 0 (loglik); q_i over *declared* cardinalities.
+ *     pen = 0.5 ln N (bic), 1 (aic), 0 (loglik); q_i over *declared* cardinalities;
+ *   - bde / k2: sum_i sum_j [ lgamma(a_ij) - lgamma(a_ij + N_ij) + sum_k ( lgamma(a_ijk + N_ijk)
+ *     - lgamma(a_ijk) ) ],  a_ijk = iss / (q_i r_i) (bde) or 1 (k2),  a_ij = r_i a_ijk.
  *
  * Pointer arguments are HOST pointers unless BIC_FLAG_DEVICE_PTRS is passed, in which case
  * every array argument of that call (inputs and outputs) is a device pointer on the context's
@@ -49,7 +51,10 @@ typedef enum {
     BIC_ERR_BAD_FAMILY = -8       /* a parent index is out of range or equals the node       */
 } bic_status;
 
-typedef enum { BIC_METRIC_BIC = 0, BIC_METRIC_LOGLIK = 1, BIC_METRIC_AIC = 2 } bic_metric;
+/* bnlearn score(type = ...) names: "bic", "loglik", "aic", "bde" (BDeu with imaginary sample size
+ * iss, see bic_set_iss), "k2".  The reference forwards the string unchanged (bnlearn.py:50,
+ * bnlearn_score.R:38); only "bic" is pinned by its tests. */
+typedef enum { BIC_METRIC_BIC = 0, BIC_METRIC_LOGLIK = 1, BIC_METRIC_AIC = 2, BIC_METRIC_BDE = 3, BIC_METRIC_K2 = 4 } bic_metric;
 
 enum {
     BIC_FLAG_DEVICE_PTRS = 1,    /* array arguments are device pointers                       */
@@ -70,6 +75,9 @@ const char *bic_last_error(const bic_ctx *ctx);
  * context's own stream.  NULL restores the own stream. */
 int bic_set_stream(bic_ctx *ctx, void *cuda_stream);
 int bic_sync(bic_ctx *ctx);
+/* Imaginary sample size of the "bde" metric (bnlearn's iss argument; default 1).  Clears cached
+ * bde terms. */
+int bic_set_iss(bic_ctx *ctx, double iss);
 
 /* ---- dataset ---------------------------------------------------------------------------
  * Replaces: data(list = dataset_name); dataset <- get(dataset_name)  (bnlearn_score.R:25-26).

@@ -24,7 +24,10 @@
 #include <omp.h>
 #endif
 
-enum { ORACLE_BIC = 0, ORACLE_LOGLIK = 1, ORACLE_AIC = 2 };
+enum { ORACLE_BIC = 0, ORACLE_LOGLIK = 1, ORACLE_AIC = 2, ORACLE_BDE = 3, ORACLE_K2 = 4 };
+
+static double g_iss = 1.0;   /* imaginary sample size of the BDeu metric (bnlearn iss) */
+void oracle_set_iss(double iss) { g_iss = iss; }
 
 int oracle_max_threads(void) {
 #ifdef _OPENMP
@@ -58,6 +61,19 @@ int oracle_family_counts(const uint8_t *codes, int64_t N, int64_t stride, const 
 
 /* sum_{jk: N_ijk > 0} N_ijk * ln(N_ijk / N_ij) - penalty(metric). */
 double oracle_score_counts(const int64_t *counts, int64_t q, int32_t r, int64_t N, int32_t metric) {
+    if (metric == ORACLE_BDE || metric == ORACLE_K2) {
+        /* bnlearn "bde" (BDeu, a_ijk = iss / (q r)) and "k2" (a_ijk = 1) */
+        double a_ijk = metric == ORACLE_BDE ? g_iss / ((double)q * (double)r) : 1.0, a_ij = a_ijk * r, s = 0.0;
+        for (int64_t j = 0; j < q; ++j) {
+            int64_t nij = 0;
+            for (int x = 0; x < r; ++x) nij += counts[j * r + x];
+            if (!nij) continue;
+            s += lgamma(a_ij) - lgamma(a_ij + (double)nij);
+            for (int x = 0; x < r; ++x)
+                if (counts[j * r + x]) s += lgamma(a_ijk + (double)counts[j * r + x]) - lgamma(a_ijk);
+        }
+        return s;
+    }
     double ll = 0.0;
     for (int64_t j = 0; j < q; ++j) {
         int64_t nij = 0;

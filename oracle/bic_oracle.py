@@ -143,10 +143,24 @@ def metric_penalty(metric: str, N: int, r: int, q: int) -> float:
     raise NotImplementedError(f"metric {metric!r}")
 
 
+def family_bd(counts: np.ndarray, a_ijk: float) -> float:
+    """Bayesian-Dirichlet family term (bnlearn "bde" = BDeu with a_ijk = iss / (q r), "k2" with
+    a_ijk = 1): sum_j [lgamma(a_ij) - lgamma(a_ij + N_ij) + sum_k (lgamma(a_ijk + N_ijk) - lgamma(a_ijk))]."""
+    from scipy.special import gammaln
+    r = counts.shape[1]
+    a_ij = a_ijk * r
+    nij = counts.sum(axis=1).astype(np.float64)
+    c = counts.astype(np.float64)
+    return float(np.sum(gammaln(a_ij) - gammaln(a_ij + nij)) + np.sum(gammaln(a_ijk + c) - gammaln(a_ijk)))
+
+
 def family_score(codes: np.ndarray, card: np.ndarray, node: int, parents: Iterable[int],
-                 metric: str = "bic") -> float:
+                 metric: str = "bic", iss: float = 1.0) -> float:
     N = codes.shape[1]
     counts = family_counts(codes, card, node, parents)
+    if metric in ("bde", "k2"):
+        q, r = counts.shape
+        return family_bd(counts, iss / (q * r) if metric == "bde" else 1.0)
     return family_loglik(counts) - metric_penalty(metric, N, int(card[node]), family_q(card, parents))
 
 

@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-METRICS = {"bic": 0, "loglik": 1, "aic": 2}
+METRICS = {"bic": 0, "loglik": 1, "aic": 2, "bde": 3, "k2": 4}
 
 
 def build(force: bool = False) -> str:
@@ -37,6 +37,8 @@ def lib():
         i64p = ctypes.POINTER(ctypes.c_int64)
         f64p = ctypes.POINTER(ctypes.c_double)
         L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_set_iss.argtypes = [ctypes.c_double]
+        L.oracle_set_iss.restype = None
         L.oracle_family_counts.argtypes = [u8p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int32,
                                            i32p, ctypes.c_int32, i64p]
         L.oracle_family_counts.restype = ctypes.c_int
@@ -52,6 +54,10 @@ def lib():
 
 def _p(a, t):
     return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def set_iss(iss: float) -> None:
+    lib().oracle_set_iss(float(iss))
 
 
 def max_threads() -> int:

@@ -511,4 +511,51 @@ def test_stream_profile_and_metric_switch(asia, asia_scorer):
     nparams = ll - aic
     assert np.allclose(bic, ll - 0.5 * np.log(5000) * nparams, rtol=1e-13)
     with pytest.raises(NotImplementedError):
-        asia_scorer.score_adjacency(adj, metric="bde")
+        asia_scorer.score_adjacency(adj, metric="mbde")
+
+
+# ------------------------------------------------------------------ bde (BDeu) and k2
+def test_bde_and_k2_match_oracle(asia, sachs):
+    """bnlearn's other decomposable count-based scores, computed as an lgamma epilogue on the same
+    count tables.  The reference pins none of them: oracle-only parity."""
+    codes, card = asia
+    fams = all_families(8)
+    node, off, par = csr_of(fams)
+    with pkg.BicScorer(codes, card) as s:
+        for metric, iss in (("bde", 1.0), ("bde", 10.0), ("k2", 1.0)):
+            s.set_iss(iss)
+            C.set_iss(iss)
+            got = s.score_families_csr(node, off, par, metric=metric)
+            assert_scores(got, C.score_families(codes, card, node, off, par, metric=metric))
+            assert got[5] == pytest.approx(O.family_score(codes, card, fams[5][0], fams[5][1], metric, iss), rel=1e-9)
+        C.set_iss(1.0)
+        s.set_iss(1.0)
+        # switching between term kinds re-counts (one kind cached at a time) and stays consistent
+        adj = synth.er_candidates(8, 500, 5, 14, None, seed=12)
+        bde = s.score_adjacency(adj, metric="bde")
+        bic = s.score_adjacency(adj, metric="bic")
+        assert np.array_equal(s.score_adjacency(adj, metric="bde"), bde)
+        assert_scores(bic, C.score_dags_adj(codes, card, adj, metric="bic"))
+        assert_scores(bde, C.score_dags_adj(codes, card, adj, metric="bde"))
+    ev = pkg.BNLearnWrapper("asia", "k2")
+    g = Graph(8, [(0, 2), (1, 3), (1, 4), (2, 5), (3, 5), (5, 6), (5, 7), (4, 7)], list(range(8)))
+    true = np.zeros((1, 8, 8), dtype=np.uint8)
+    for u, v in g.get_edgelist():
+        true[0, u, v] = 1
+    assert ev.score(g) == pytest.approx(C.score_dags_adj(codes, card, true, metric="k2")[0], rel=1e-9)
+    # large tables (HBM class) and a big dataset through the derive path
+    codes, card = sachs
+    with pkg.BicScorer(codes, card, metric="bde", iss=5.0) as s:
+        C.set_iss(5.0)
+        f2 = [(0, list(range(1, 11))), (3, [0, 1, 2, 4, 5, 6, 7, 8]), (4, [1])]
+        node, off, par = csr_of(f2)
+        assert_scores(s.score_families_csr(node, off, par), C.score_families(codes, card, node, off, par, metric="bde"))
+        C.set_iss(1.0)
+    N = 1_100_000
+    adj, card, cpts = synth.make_network(8, 10, 3, [2, 3], seed=51)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(52))
+    dags = synth.er_candidates(8, 200, 7, 16, 5, seed=53)
+    with pkg.BicScorer(codes, card, metric="k2") as s:
+        got = s.score_adjacency(dags)
+        assert s.profile()["families_derived"] > 0
+        assert_scores(got[:25], C.score_dags_adj(codes, card, dags[:25], metric="k2"))

@@ -60,7 +60,7 @@ def test_product_never_imports_oracle():
 
 def test_unknown_metric_and_dataset():
     with pytest.raises(NotImplementedError):
-        pkg.BNLearnWrapper("asia", "bde")
+        pkg.BNLearnWrapper("asia", "mbde")
     with pytest.raises(ValueError):
         pkg.load_dataset("no_such_dataset")
     codes, card, names = pkg.load_dataset("asia")

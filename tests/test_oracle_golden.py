@@ -97,3 +97,33 @@ def test_acyclic_and_unobserved_configs(sachs):
     s = O.family_score(codes, card, 0, parents, "bic")
     ll = O.family_score(codes, card, 0, parents, "loglik")
     assert s == pytest.approx(ll - 0.5 * np.log(5000) * 2 * 3 ** 9)
+
+
+def test_bd_metrics_numpy_vs_c(asia, sachs):
+    """bde / k2 are unpinned by the reference (no value in its tree); the two restatements at
+    least agree with each other and with the closed form on a tiny table."""
+    import math
+    rng = np.random.default_rng(5)
+    for codes, card in (asia, sachs):
+        n = codes.shape[0]
+        fams = []
+        for _ in range(20):
+            i = int(rng.integers(n))
+            k = int(rng.integers(0, 5))
+            fams.append((i, sorted(rng.choice([p for p in range(n) if p != i], size=k, replace=False).tolist())))
+        node = np.array([f[0] for f in fams], dtype=np.int32)
+        off = np.zeros(len(fams) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(f[1]) for f in fams])
+        par = np.array([p for f in fams for p in f[1]], dtype=np.int32)
+        for metric, iss in (("bde", 1.0), ("bde", 7.5), ("k2", 1.0)):
+            C.set_iss(iss)
+            got = C.score_families(codes, card, node, off, par, metric=metric)
+            want = np.array([O.family_score(codes, card, i, ps, metric, iss) for i, ps in fams])
+            assert np.allclose(got, want, rtol=1e-11, atol=0)
+        C.set_iss(1.0)
+    # K2 of a root node with counts (n0, n1): lgamma(2) - lgamma(N + 2) + lgamma(n0 + 1) + lgamma(n1 + 1)
+    codes, card = asia
+    n1 = int(codes[0].sum())
+    n0 = codes.shape[1] - n1
+    want = math.lgamma(2) - math.lgamma(n0 + n1 + 2) + math.lgamma(n0 + 1) + math.lgamma(n1 + 1)
+    assert O.family_score(codes, card, 0, [], "k2") == pytest.approx(want, rel=1e-13)
