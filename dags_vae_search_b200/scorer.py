@@ -220,12 +220,21 @@ class BicScorer:
                    return_invalid: bool = False):
         """Reference candidate wire format (``src/toolkit/labeled.py:116-154``): ``labels[b, v]`` =
         BN variable of vertex v, bit u of ``ebits[b, v]`` <=> edge vertex u -> vertex v."""
+        inv = ctypes.c_int64(0)
+        if _is_torch(labels) and labels.is_cuda:     # decoder output that never leaves the GPU
+            import torch
+            lab = labels.reshape(-1, self.n).to(torch.uint8).contiguous()
+            eb = ebits.reshape(-1, self.n).to(torch.int32).contiguous()     # bit pattern of the uint32 words
+            out = torch.empty(lab.shape[0], dtype=torch.float64, device=lab.device)
+            self._check(self._lib.bic_score_dags_wire(self._ctx, lab.data_ptr(), eb.data_ptr(), lab.shape[0],
+                                                      self._metric(metric), out.data_ptr(), ctypes.byref(inv),
+                                                      self._flags(True, no_cache, True)))
+            return (out, int(inv.value)) if return_invalid else out
         labels = np.ascontiguousarray(labels, dtype=np.uint8).reshape(-1, self.n)
         ebits = np.ascontiguousarray(ebits, dtype=np.uint32).reshape(-1, self.n)
         if labels.shape != ebits.shape:
             raise ValueError("labels and ebits must both be [B, n]")
         out = np.empty(labels.shape[0], dtype=np.float64)
-        inv = ctypes.c_int64(0)
         self._check(self._lib.bic_score_dags_wire(self._ctx, labels.ctypes.data, ebits.ctypes.data, labels.shape[0],
                                                   self._metric(metric), out.ctypes.data, ctypes.byref(inv),
                                                   self._flags(True, no_cache, False)))

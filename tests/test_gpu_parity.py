@@ -559,3 +559,36 @@ def test_bde_and_k2_match_oracle(asia, sachs):
         got = s.score_adjacency(dags)
         assert s.profile()["families_derived"] > 0
         assert_scores(got[:25], C.score_dags_adj(codes, card, dags[:25], metric="k2"))
+
+
+# ------------------------------------------------------- search loop on top of the scorer
+def test_hill_climb_search_loop(asia, asia_scorer):
+    """Config 3's "search loop with batched scoring": greedy hill climbing over single-edge moves.
+    Every iteration is one batched call; the search must be monotone, end in a local optimum that
+    the oracle confirms, beat the empty graph by a wide margin, and run almost entirely out of the
+    family-score cache.  (The path itself is not compared with a CPU run: BIC is score-equivalent,
+    so exact ties between edge orientations are broken by rounding.)"""
+    from dags_vae_search_b200 import search
+    codes, card = asia
+    asia_scorer.cache_clear()
+    best, score, trace = search.hill_climb(asia_scorer)
+    assert O.is_acyclic(best) and len(trace) >= 5
+    steps = [s for _, s in trace]
+    assert all(b > a for a, b in zip(steps, steps[1:]))
+    assert score == pytest.approx(O.score_adjacency(codes, card, best), rel=RTOL)
+    empty = O.score_adjacency(codes, card, np.zeros((8, 8), dtype=np.uint8))
+    assert score > empty + 1000 and score > -11200          # the true DAG scores -11109.74 on this sample
+    cand, _ = search.neighbours(best)
+    assert all(O.is_acyclic(a) for a in cand[:50])
+    assert (asia_scorer.score_adjacency(cand) <= score + 1e-6).all()      # local optimum
+    st = asia_scorer.cache_stats()
+    assert st["misses"] <= 1024 and st["lookups"] > 20 * st["misses"]
+    # wire format straight from CUDA tensors (decoder output that never leaves the GPU)
+    import torch
+    labels = np.tile(np.arange(8, dtype=np.uint8), (3, 1))
+    ebits = np.zeros((3, 8), dtype=np.uint32)
+    ebits[1, 2] = 0b11
+    ebits[2, 7] = 0b1010101
+    host = asia_scorer.score_wire(labels, ebits)
+    dev = asia_scorer.score_wire(torch.from_numpy(labels).cuda(), torch.from_numpy(ebits.astype(np.int32)).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
