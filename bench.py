@@ -395,7 +395,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # roofline of the dominant kernel = the count-kernel class that took most of the step
-    kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory, lane replicas <= 512 cells)",
+    kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory; 32 lane replicas <= 192 cells, 16 <= 384)",
                "k_count<512,false> (tables <= 12288 cells in shared memory)",
                "k_count<512,false> (tables <= 49152 cells in shared memory)",
                "k_count<256,true> (tables in HBM, L2 atomics)"]

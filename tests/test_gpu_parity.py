@@ -592,3 +592,25 @@ def test_hill_climb_search_loop(asia, asia_scorer):
     host = asia_scorer.score_wire(labels, ebits)
     dev = asia_scorer.score_wire(torch.from_numpy(labels).cuda(), torch.from_numpy(ebits.astype(np.int32)).cuda())
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_degenerate_shapes():
+    """One variable, one row, all-constant columns, a single DAG."""
+    with pkg.BicScorer(np.array([[0, 1, 1, 0, 1]], dtype=np.uint8), np.array([2], dtype=np.int32)) as s:
+        got = s.score_adjacency(np.zeros((1, 1, 1), dtype=np.uint8))
+        want = 2 * np.log(2 / 5) + 3 * np.log(3 / 5) - 0.5 * np.log(5)
+        assert got[0] == pytest.approx(want, rel=1e-12)
+        out, bad = s.score_adjacency(np.ones((1, 1, 1), dtype=np.uint8), return_invalid=True)   # self loop
+        assert bad == 1 and np.isnan(out[0])
+    codes = np.zeros((3, 1), dtype=np.uint8)
+    with pkg.BicScorer(codes, np.array([1, 1, 1], dtype=np.int32)) as s:       # one row, constant variables
+        adj = np.zeros((1, 3, 3), dtype=np.uint8)
+        adj[0, 0, 1] = adj[0, 1, 2] = 1
+        assert s.score_adjacency(adj)[0] == 0.0
+        assert s.family_counts(2, [0, 1]).tolist() == [[1]]
+    with pkg.BicScorer(codes, np.array([2, 3, 4], dtype=np.int32)) as s:       # one row, declared wider
+        adj = np.zeros((1, 3, 3), dtype=np.uint8)
+        adj[0, 0, 2] = adj[0, 1, 2] = 1
+        # ln N = 0 with one row: BIC == loglik == 0; AIC charges the declared parameters
+        assert s.score_adjacency(adj)[0] == 0.0
+        assert s.score_adjacency(adj, metric="aic")[0] == -(1 + 2 + 3 * 2 * 3)
