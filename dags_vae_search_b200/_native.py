@@ -31,7 +31,7 @@ SYMBOLS = [
     "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_sync", "bic_set_iss",
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
-    "bic_cache_stats", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
+    "bic_cache_stats", "bic_cache_export", "bic_cache_import", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
     "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy",
 ]
 
@@ -105,6 +105,8 @@ def lib() -> ctypes.CDLL:
     L.bic_cache_clear.argtypes = [vp]
     L.bic_cache_reserve.argtypes = [vp, i64]
     L.bic_cache_stats.argtypes = [vp, ctypes.POINTER(CacheStats)]
+    L.bic_cache_export.argtypes = [vp, vp, vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i32)]
+    L.bic_cache_import.argtypes = [vp, vp, vp, vp, i64, i32]
     L.bic_profile_enable.argtypes = [vp, ctypes.c_int]
     L.bic_profile_reset.argtypes = [vp]
     L.bic_profile_get.argtypes = [vp, ctypes.POINTER(Profile)]

@@ -884,6 +884,47 @@ int bic_cache_stats(bic_ctx *c, bic_cache_stats_t *out) {
     return BIC_OK;
 }
 
+int bic_cache_export(bic_ctx *c, uint64_t *keys, double *terms, double *nparams, int64_t capacity, int64_t *families,
+                     int32_t *kind) {
+    if (!c || !families) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *families = c->reg_count;
+    if (kind) *kind = c->cache_mode;
+    if (capacity == 0) return BIC_OK;
+    if (capacity < c->reg_count || !keys || !terms || !nparams) return fail(c, BIC_ERR_ARG, "export buffers too small or NULL");
+    if (!c->reg_count) return BIC_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(keys, c->regkeys, (size_t)c->reg_count * c->Wk * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(terms, c->reg_ll, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(nparams, c->reg_np, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BIC_OK;
+}
+
+int bic_cache_import(bic_ctx *c, const uint64_t *keys, const double *terms, const double *nparams, int64_t families,
+                     int32_t kind) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->data) return fail(c, BIC_ERR_NO_DATASET, "no dataset: call bic_set_dataset first");
+    if (families < 0 || kind < 0 || kind > 2 || (families > 0 && (!keys || !terms || !nparams)))
+        return fail(c, BIC_ERR_ARG, "bad import arguments");
+    for (int64_t f = 0; f < families; ++f)
+        if (keys[f * c->Wk] >= (uint64_t)c->n) return fail(c, BIC_ERR_ARG, "imported key names a node outside the dataset");
+    CU(cudaSetDevice(c->device));
+    TRY(cache_clear(c));
+    c->cache_mode = kind;
+    if (!families) return BIC_OK;
+    TRY(cache_ensure(c, families));
+    CU(cudaMemcpyAsync(c->regkeys, keys, (size_t)families * c->Wk * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->reg_ll, terms, (size_t)families * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->reg_np, nparams, (size_t)families * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_rehash<<<nblk(families, 256), 256, 0, c->stream>>>(c->regkeys, c->Wk, families, c->table, (u32)(c->table_cap - 1)); LAUNCH(c);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->reg_count = families;
+    return BIC_OK;
+}
+
 int bic_profile_enable(bic_ctx *c, int on) {
     if (!c) return BIC_ERR_ARG;
     std::lock_guard<std::mutex> lk(c->mu);

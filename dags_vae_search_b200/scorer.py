@@ -252,6 +252,38 @@ class BicScorer:
         self._check(self._lib.bic_cache_stats(self._ctx, ctypes.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in nat.CacheStats._fields_}
 
+    def save_cache(self, path: str) -> int:
+        """Checkpoint the family-score cache (keys + terms) to an ``.npz``; returns the family count."""
+        import hashlib
+        fam, kind = ctypes.c_int64(0), ctypes.c_int32(0)
+        self._check(self._lib.bic_cache_export(self._ctx, None, None, None, 0, ctypes.byref(fam), ctypes.byref(kind)))
+        F, Wk = int(fam.value), 1 + (self.n + 63) // 64
+        keys = np.zeros((max(F, 1), Wk), dtype=np.uint64)
+        terms = np.zeros(max(F, 1), dtype=np.float64)
+        nparams = np.zeros(max(F, 1), dtype=np.float64)
+        if F:
+            self._check(self._lib.bic_cache_export(self._ctx, keys.ctypes.data, terms.ctypes.data, nparams.ctypes.data, F,
+                                                   ctypes.byref(fam), ctypes.byref(kind)))
+        tag = hashlib.sha256(np.asarray([self.n, self.N], dtype=np.int64).tobytes() + self.card.tobytes()).hexdigest()
+        np.savez_compressed(path, keys=keys[:F], terms=terms[:F], nparams=nparams[:F], kind=np.int32(kind.value),
+                            dataset_tag=np.array(tag), n=np.int64(self.n), N=np.int64(self.N))
+        return F
+
+    def load_cache(self, path: str) -> int:
+        """Resume from ``save_cache``: replaces the cache content.  Refuses a checkpoint made with
+        another dataset shape / cardinalities."""
+        import hashlib
+        d = np.load(path)
+        tag = hashlib.sha256(np.asarray([self.n, self.N], dtype=np.int64).tobytes() + self.card.tobytes()).hexdigest()
+        if str(d["dataset_tag"]) != tag:
+            raise ValueError("cache checkpoint was made with a different dataset (n, N or cardinalities differ)")
+        keys = np.ascontiguousarray(d["keys"], dtype=np.uint64)
+        terms = np.ascontiguousarray(d["terms"], dtype=np.float64)
+        nparams = np.ascontiguousarray(d["nparams"], dtype=np.float64)
+        self._check(self._lib.bic_cache_import(self._ctx, keys.ctypes.data, terms.ctypes.data, nparams.ctypes.data,
+                                               len(terms), int(d["kind"])))
+        return len(terms)
+
     # ----------------------------------------------------------------- profiling
     def profile_enable(self, on: bool = True) -> None:
         self._check(self._lib.bic_profile_enable(self._ctx, 1 if on else 0))

@@ -130,6 +130,17 @@ typedef struct {
 int bic_cache_clear(bic_ctx *ctx);
 int bic_cache_reserve(bic_ctx *ctx, int64_t families);
 int bic_cache_stats(bic_ctx *ctx, bic_cache_stats_t *out);
+/* Checkpoint / resume of a long search (the reference checkpoints only its VAE,
+ * experiments/01_bn_asia/main.py:187-188; its scorer is stateless).  Export copies the registry
+ * to HOST buffers: keys [families][1 + ceil(n/64)] (word 0 = node, then the parent bitmask),
+ * terms[families] (log-likelihood, or the bde / k2 term) and nparams[families]; *kind receives
+ * what the terms are (0 log-likelihood, 1 bde, 2 k2).  Pass capacity = 0 to only query
+ * *families.  Import replaces the cache content; the caller is responsible for using it with
+ * the same dataset (and iss). */
+int bic_cache_export(bic_ctx *ctx, uint64_t *keys, double *terms, double *nparams, int64_t capacity,
+                     int64_t *families, int32_t *kind);
+int bic_cache_import(bic_ctx *ctx, const uint64_t *keys, const double *terms, const double *nparams,
+                     int64_t families, int32_t kind);
 
 /* ---- profiling (CUDA events on the launching stream, around the family-count kernels) --- */
 typedef struct {

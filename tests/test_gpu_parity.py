@@ -614,3 +614,26 @@ def test_degenerate_shapes():
         # ln N = 0 with one row: BIC == loglik == 0; AIC charges the declared parameters
         assert s.score_adjacency(adj)[0] == 0.0
         assert s.score_adjacency(adj, metric="aic")[0] == -(1 + 2 + 3 * 2 * 3)
+
+
+def test_cache_checkpoint_resume(sachs, tmp_path):
+    """Checkpoint / resume of a search: the family cache survives a process restart."""
+    codes, card = sachs
+    dags = synth.er_candidates(11, 5000, 10, 25, None, seed=61)
+    path = str(tmp_path / "cache.npz")
+    with pkg.BicScorer(codes, card) as s:
+        first = s.score_adjacency(dags)
+        saved = s.save_cache(path)
+        assert saved == s.cache_stats()["families"] > 1000
+    with pkg.BicScorer(codes, card) as s2:
+        assert s2.load_cache(path) == saved
+        again = s2.score_adjacency(dags)
+        st = s2.cache_stats()
+        assert np.array_equal(again, first) and st["misses"] == 0 and st["families"] == saved
+        # new families still get counted and join the restored ones
+        more = synth.er_candidates(11, 500, 10, 25, None, seed=62)
+        got = s2.score_adjacency(more)
+        assert_scores(got[:20], C.score_dags_adj(codes, card, more[:20]))
+    with pkg.BicScorer(codes[:, :4000], card) as s3:
+        with pytest.raises(ValueError, match="different dataset"):
+            s3.load_cache(path)
