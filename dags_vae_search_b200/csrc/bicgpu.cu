@@ -332,8 +332,9 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         CU(c->table_off.ensure((size_t)njobs * sizeof(u64)));
         k_table_need<<<nblk(njobs, 256), 256, 0, c->stream>>>(c->cells_arr.as<u32>(), (u32)njobs, na, c->need.as<u32>()); LAUNCH(c);
         TRY((scan_excl<u32, u64>(c, c->need.as<u32>(), njobs, c->table_off.as<u64>(), &c->d_hdr->table_cells, c->bsum64)));
-        TRY(header_fetch(c));
-        size_t cells = (size_t)c->h_hdr->table_cells;
+        // no second host synchronisation: the first header already carries the sum of all cells,
+        // an upper bound of what the scan assigns (exact when every table lives in HBM)
+        size_t cells = (size_t)h.cells_all;
         CU(c->arena.ensure(std::max<size_t>(cells, 1) * sizeof(u32)));
         CU(cudaMemsetAsync(c->arena.p, 0, std::max<size_t>(cells, 1) * sizeof(u32), c->stream));
     }
@@ -350,7 +351,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.done = c->done.as<u32>();
     a.ll_out = ll_out; a.np_out = np_out;
     a.reduce = sharded ? 0 : 1;
-    a.donor = with_donors ? c->donor.as<int>() : nullptr;
+    a.donor = (with_donors && n_derived) ? c->donor.as<int>() : nullptr;
     a.bd_mode = c->cache_mode;
     a.iss = c->iss;
     u32 class_count[NCLASS];
@@ -406,7 +407,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     c->prof.families_derived += n_derived;
 
     if (sharded) {
-        size_t cells = (size_t)c->h_hdr->table_cells;
+        size_t cells = (size_t)h.cells_all;   // all tables live in HBM when sharded: exact
         if (cells) {
             int rc = g_nccl.AllReduce(c->arena.p, c->arena.p, cells, NCCL_UINT32, NCCL_SUM, c->comm, c->stream);
             if (rc != 0) return fail(c, BIC_ERR_NCCL, std::string("ncclAllReduce(count tables): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
@@ -457,9 +458,9 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
         k_announce<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
                                              c->d_card, c->donor_best.as<u64>()); LAUNCH(c);
     }
-    k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c);
+    if (derive) { k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c); }
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
-                                             c->donor.as<int>(), c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
+                                             derive ? c->donor.as<int>() : nullptr, c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
                                              c->derived_list.as<int>()); LAUNCH(c);
     CU(cudaGetLastError());
     TRY(header_fetch(c));

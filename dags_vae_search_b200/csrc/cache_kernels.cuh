@@ -298,6 +298,7 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
         return;
     }
     cells_arr[j] = (u32)cells;
+    atomicAdd(&hdr->cells_all, cells);
     int cls = cells <= CLASS0_CELLS ? 0 : cells <= CLASS1_CELLS ? 1 : cells <= CLASS2_CELLS ? 2 : 3;
     u32 pos = atomicAdd(&hdr->class_count[cls], 1u);
     class_jobs[(long long)cls * max_jobs + pos] = (int)j;
@@ -417,13 +418,14 @@ __global__ void k_pick_donor(const u64 *__restrict__ best, const Header *hdr, in
 }
 
 // Describe the new families: counted ones get a count job, derived ones go to the derive list.
+// donor == nullptr: derivation is off, every new family is counted.
 __global__ void k_describe_new(const u64 *__restrict__ regkeys, int W64, long long base, const int *__restrict__ card,
                                long long N, u32 max_jobs, Header *hdr, const int *__restrict__ donor,
                                u32 *cells_arr, int *class_jobs, int *derived_list) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= hdr->f_new) return;
     const u64 *key = regkeys + (base + j) * (W64 + 1);
-    if (donor[j] < 0) {
+    if (!donor || donor[j] < 0) {
         describe_family(key, W64, card, N, (u32)j, max_jobs, hdr, cells_arr, class_jobs);
         return;
     }
@@ -441,6 +443,7 @@ __global__ void k_describe_new(const u64 *__restrict__ regkeys, int W64, long lo
         }
     }
     cells_arr[j] = (u32)cells;
+    atomicAdd(&hdr->cells_all, cells);
     derived_list[atomicAdd(&hdr->n_derived, 1u)] = (int)j;
     atomicAdd(&hdr->lvl_count[pc], 1u);
 }

@@ -35,6 +35,7 @@ struct Header {
     u32 pad;
     u64 alg_bytes[NCLASS];     // sum (k+1)*N + 4*q*r over the new families, per class
     u64 table_cells;           // cells of all count tables that must live in HBM (scan total)
+    u64 cells_all;             // cells of every described family: upper bound of table_cells, exact when all tables live in HBM
     u32 n_derived;             // new families whose table is marginalised from a counted superset
     u32 lvl_count[DERIVE_LEVELS];   // of those, by number of parents
 };
