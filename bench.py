@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debug only)")
     ap.add_argument("--batch", type=int, default=0, help="override DAGs per GPU per step (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="family", choices=["family", "independent"],
+                    help="N > 1, candidate-sharded workloads: 'family' = the ranks' batches form one global batch whose "
+                         "unique families are split over the GPUs; 'independent' = every rank scores its own batch alone")
     return ap.parse_args()
 
 
@@ -285,11 +288,21 @@ def main():
     scorer = pkg.BicScorer(codes, card, device=local_rank)
     del codes
     torch.cuda.empty_cache()
-    scorer.set_stream(torch.cuda.current_stream().cuda_stream)
     n = cfg["n"]
-    if sharded and world > 1:
-        from dags_vae_search_b200 import dist as bdist
-        bdist.init_row_sharding(scorer)
+    dbg = (lambda *a: print(f"[bench r{rank}]", *a, file=sys.stderr, flush=True)) if os.environ.get("BENCH_DEBUG") else (lambda *a: None)
+    from dags_vae_search_b200 import dist as bdist
+    famshard = (not sharded) and world > 1 and args.multi == "family"
+    if world > 1 and (sharded or famshard):
+        # the scorer keeps its own (non-blocking) stream when its NCCL communicator is active: sharing
+        # torch's legacy default stream between two communicators hung once (2 GPUs, all-gather + all-reduce
+        # interleaved).  Calls are synchronous, so the CUDA events on torch's stream still bracket them.
+        if sharded:
+            bdist.init_row_sharding(scorer)
+        else:
+            bdist.init_family_sharding(scorer)
+    else:
+        scorer.set_stream(torch.cuda.current_stream().cuda_stream)
+    dbg("scorer ready, family sharding" if famshard else "scorer ready")
 
     total_steps = args.warmup + args.steps
     dev_out = torch.empty(batch, dtype=torch.float64, device=device)
@@ -313,17 +326,38 @@ def main():
             scorer.cache_clear()
             return scorer.score_csr_into(host_csr[s][0].data_ptr(), host_csr[s][1].data_ptr(), batch, host_out.data_ptr(), device=False)
     else:
-        host_adj = [torch.from_numpy(candidate_batch(cfg, batch, s, rank, world)).pin_memory() for s in range(total_steps)]
-        dev_adj = [a.to(device) for a in host_adj]
-        h2d_bytes = batch * n * n
+        if famshard:
+            # one global batch per step = the concatenation of every rank's fresh batch.  Every rank
+            # generates all of it (same seeds), so no collective of another communicator runs inside the
+            # timed region; a search would all-gather its decoded candidates instead (dist.all_gather_batches)
+            host_adj = [torch.from_numpy(np.concatenate([candidate_batch(cfg, batch, s, r, world) for r in range(world)])).pin_memory()
+                        for s in range(total_steps)]
+            dev_adj = [a.to(device) for a in host_adj]
+            h2d_bytes = batch * world * n * n
+            glob_out = torch.empty(batch * world, dtype=torch.float64, device=device)
+            glob_host_out = torch.empty(batch * world, dtype=torch.float64).pin_memory()
 
-        def step_resident(s):
-            scorer.cache_clear()
-            return scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
+            def step_resident(s):
+                scorer.cache_clear()
+                return scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch * world, glob_out.data_ptr(), device=True)
 
-        def step_e2e(s):
-            scorer.cache_clear()
-            return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False)
+            def step_e2e(s):
+                scorer.cache_clear()
+                bad = scorer.score_adjacency_into(host_adj[s].data_ptr(), batch * world, glob_host_out.data_ptr(), device=False)
+                host_out.copy_(glob_host_out[rank * batch:(rank + 1) * batch])
+                return bad
+        else:
+            host_adj = [torch.from_numpy(candidate_batch(cfg, batch, s, rank, world)).pin_memory() for s in range(total_steps)]
+            dev_adj = [a.to(device) for a in host_adj]
+            h2d_bytes = batch * n * n
+
+            def step_resident(s):
+                scorer.cache_clear()
+                return scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
+
+            def step_e2e(s):
+                scorer.cache_clear()
+                return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False)
 
     # L2 flush between steps: the 2-bit packed copy of the alarm dataset (92.5 MB) would otherwise
     # still sit in the 126 MB L2 when the next step starts.  Writing 256 MB evicts it (~50 us/step).
@@ -332,6 +366,7 @@ def main():
     def timed(step_fn):
         for s in range(args.warmup):
             step_fn(s)
+            dbg("warmup step", s, step_fn.__name__)
         scorer.profile_enable(True)
         scorer.profile_reset()
         sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -341,6 +376,7 @@ def main():
         for s in range(args.warmup, total_steps):
             flush_buf.zero_()
             step_fn(s)
+            dbg("timed step", s, step_fn.__name__)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -352,7 +388,7 @@ def main():
         return float(ms.item()), prof, clocks
 
     ms_res, prof, clocks = timed(step_resident)
-    checksum = float(dev_out.sum().item())
+    checksum = float((glob_out if famshard else dev_out).sum().item())
     ms_e2e, prof_e2e, _ = timed(step_e2e)
     assert not np.isnan(host_out.numpy()).any()
 
@@ -366,6 +402,8 @@ def main():
         for s in range(total_steps):
             if sharded:
                 scorer.score_csr_into(dev_csr[s][0].data_ptr(), dev_csr[s][1].data_ptr(), batch, dev_out.data_ptr(), device=True)
+            elif famshard:
+                scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch * world, glob_out.data_ptr(), device=True)
             else:
                 scorer.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
         e1.record()
@@ -374,7 +412,9 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
+    dbg("stream")
     ms_stream = run_stream()
+    dbg("stream done")
     stream_stats = scorer.cache_stats()
 
     if rank != 0:
@@ -418,9 +458,12 @@ def main():
                    "l2": (f"L2 flushed before every timed step (256 MB written inside the timed region); dataset {rows * n / 1e6:.0f} MB uint8"
                           + (f" + {rows * n / 4e6:.0f} MB 2-bit packed copy, re-read by every streamed family within a step" if rows >= (1 << 20) else "")),
                    "parallelism": (f"row-sharded x{world} ({rows} rows per GPU, {rows * world} in total), ncclAllReduce(uint32) of count tables"
-                                   if sharded else f"candidate-sharded x{world}, dataset replicated")},
+                                   if sharded else (f"candidate-sharded x{world}, dataset replicated; the ranks' batches form one global batch per step "
+                                                    f"({batch * world} DAGs): deduplicated identically on every rank, unique families split "
+                                                    "over the GPUs, family terms combined with ncclAllReduce(double); each rank holds the whole global batch" if famshard
+                                                    else f"candidate-sharded x{world}, dataset replicated, every rank scores its own batch independently"))},
         "e2e": {"value": dags / (ms_e2e * 1e-3), "unit": "DAGs/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": batch * 8},
+                "d2h_bytes_per_step": batch * 8 * (world if famshard else 1)},
         "gpu_launches": prof["kernel_launches"],
         "family_count_rows_per_sec": prof["rows_counted"] / (prof["count_ms"] * 1e-3) if prof["count_ms"] > 0 else None,
         "families_counted_per_step": prof["families_counted"] / args.steps,

@@ -32,7 +32,7 @@ SYMBOLS = [
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
     "bic_cache_stats", "bic_cache_export", "bic_cache_import", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
-    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy",
+    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy", "bic_comm_mode",
 ]
 
 
@@ -113,6 +113,7 @@ def lib() -> ctypes.CDLL:
     L.bic_comm_unique_id.argtypes = [vp]
     L.bic_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     L.bic_comm_destroy.argtypes = [vp]
+    L.bic_comm_mode.argtypes = [vp, ctypes.c_int]
     for name in SYMBOLS:
         if name not in ("bic_last_error",):
             getattr(L, name).restype = ctypes.c_int

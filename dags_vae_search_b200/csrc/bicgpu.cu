@@ -84,7 +84,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 std::mutex g_nccl_mu;
-constexpr int NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_SUM = 0;   // nccl.h: ncclDataType_t / ncclRedOp_t
+constexpr int NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // nccl.h: ncclDataType_t / ncclRedOp_t
 
 }  // namespace
 
@@ -148,6 +148,7 @@ struct bic_ctx {
     // row sharding
     nccl_comm comm = nullptr;
     int rank_id = 0, world = 1;
+    int comm_mode = 0;       // BIC_SHARD_ROWS or BIC_SHARD_FAMILIES
     bool ntotal_dirty = true;
 };
 
@@ -284,7 +285,7 @@ int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
 int refresh_ntotal(bic_ctx *c) {
     if (!c->ntotal_dirty) return BIC_OK;
     c->N_total = c->N;
-    if (c->comm) {
+    if (c->comm && c->comm_mode == BIC_SHARD_ROWS) {
         long long *d = nullptr;
         CU(cudaMalloc(&d, sizeof(long long)));
         CU(cudaMemcpyAsync(d, &c->N, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
@@ -303,7 +304,7 @@ int refresh_ntotal(bic_ctx *c) {
 int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, long long max_jobs,
               double *ll_out, double *np_out, bool want_tables, bool with_donors) {
     const Header &h = *c->h_hdr;
-    const bool sharded = c->comm != nullptr;
+    const bool sharded = c->comm != nullptr && c->comm_mode == BIC_SHARD_ROWS;
     const u32 n_derived = with_donors ? h.n_derived : 0;
     u32 lvl_count[DERIVE_LEVELS];
     for (int l = 0; l < DERIVE_LEVELS; ++l) lvl_count[l] = with_donors ? h.lvl_count[l] : 0;   // header is re-fetched below
@@ -402,8 +403,10 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         c->prof.class_alg_bytes[k] += (long long)class_alg[k];
         c->prof.alg_bytes += (long long)class_alg[k];
     }
-    c->prof.families_counted += njobs - n_derived;
-    c->prof.rows_counted += (njobs - n_derived) * c->N;
+    long long counted = 0;   // jobs of this rank (all new families unless they are sharded over the ranks)
+    for (int k = 0; k < NCLASS; ++k) counted += class_count[k];
+    c->prof.families_counted += counted;
+    c->prof.rows_counted += counted * c->N;
     c->prof.families_derived += n_derived;
 
     if (sharded) {
@@ -453,6 +456,7 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     CU(c->donor_best.ensure((size_t)T * sizeof(u64)));   // (joint cells, index) of the cheapest donor announced so far
     CU(c->derived_list.ensure((size_t)T * sizeof(int)));
     const int derive = (c->tune.derive && !no_derive && c->N >= c->tune.derive_min_rows) ? 1 : 0;
+    const bool famshard = c->comm != nullptr && c->comm_mode == BIC_SHARD_FAMILIES && c->world > 1;
     if (derive) {
         CU(cudaMemsetAsync(c->donor_best.p, 0xff, (size_t)T * sizeof(u64), c->stream));
         k_announce<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
@@ -461,7 +465,7 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     if (derive) { k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c); }
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
                                              derive ? c->donor.as<int>() : nullptr, c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
-                                             c->derived_list.as<int>()); LAUNCH(c);
+                                             c->derived_list.as<int>(), c->rank_id, famshard ? c->world : 1); LAUNCH(c);
     CU(cudaGetLastError());
     TRY(header_fetch(c));
     long long f_new = c->h_hdr->f_new;
@@ -473,7 +477,16 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
         return rc;
     }
     if (f_new) {
+        if (famshard) {   // terms of the families other ranks own arrive through the all-reduce as x + 0 + ... + 0
+            CU(cudaMemsetAsync(c->reg_ll + c->reg_count, 0, (size_t)f_new * sizeof(double), c->stream));
+            CU(cudaMemsetAsync(c->reg_np + c->reg_count, 0, (size_t)f_new * sizeof(double), c->stream));
+        }
         rc = run_count(c, c->regkeys, c->reg_count, f_new, T, c->reg_ll, c->reg_np, false, true);
+        if (rc == BIC_OK && famshard) {
+            int e1 = g_nccl.AllReduce(c->reg_ll + c->reg_count, c->reg_ll + c->reg_count, (size_t)f_new, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            int e2 = g_nccl.AllReduce(c->reg_np + c->reg_count, c->reg_np + c->reg_count, (size_t)f_new, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            if (e1 != 0 || e2 != 0) rc = fail(c, BIC_ERR_NCCL, "ncclAllReduce(family terms) failed");
+        }
         if (rc != BIC_OK) { cache_clear(c); return rc; }
         c->reg_count += f_new;
     }
@@ -979,6 +992,17 @@ int bic_comm_init(bic_ctx *c, const uint8_t id[128], int rank, int world) {
     c->world = world;
     c->ntotal_dirty = true;
     TRY(cache_clear(c));   // cached terms were computed on this rank's rows only
+    return BIC_OK;
+}
+
+int bic_comm_mode(bic_ctx *c, int mode) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (mode != BIC_SHARD_ROWS && mode != BIC_SHARD_FAMILIES) return fail(c, BIC_ERR_ARG, "unknown sharding mode");
+    CU(cudaSetDevice(c->device));
+    c->comm_mode = mode;
+    c->ntotal_dirty = true;
+    TRY(cache_clear(c));
     return BIC_OK;
 }
 

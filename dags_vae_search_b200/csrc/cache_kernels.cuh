@@ -419,11 +419,22 @@ __global__ void k_pick_donor(const u64 *__restrict__ best, const Header *hdr, in
 
 // Describe the new families: counted ones get a count job, derived ones go to the derive list.
 // donor == nullptr: derivation is off, every new family is counted.
+// world > 1 (family sharding): a family belongs to the rank that owns the root of its donor chain,
+// so a derived family and every table it is derived from live on the same rank; families of other
+// ranks get no job and no table here.
 __global__ void k_describe_new(const u64 *__restrict__ regkeys, int W64, long long base, const int *__restrict__ card,
                                long long N, u32 max_jobs, Header *hdr, const int *__restrict__ donor,
-                               u32 *cells_arr, int *class_jobs, int *derived_list) {
+                               u32 *cells_arr, int *class_jobs, int *derived_list, int rank, int world) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= hdr->f_new) return;
+    if (world > 1) {
+        long long root = j;
+        while (donor && donor[root] >= 0) root = donor[root];
+        if ((int)(mix64((u64)root) % (u64)world) != rank) {
+            cells_arr[j] = 0;
+            return;
+        }
+    }
     const u64 *key = regkeys + (base + j) * (W64 + 1);
     if (!donor || donor[j] < 0) {
         describe_family(key, W64, card, N, (u32)j, max_jobs, hdr, cells_arr, class_jobs);

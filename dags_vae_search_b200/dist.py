@@ -61,3 +61,21 @@ def init_row_sharding(scorer, group=None) -> None:
     import torch.distributed as dist
     uid = broadcast_unique_id(group)
     scorer.init_row_sharding(dist.get_rank(group), dist.get_world_size(group), uid)
+
+
+def init_family_sharding(scorer, group=None) -> None:
+    """Families of a global candidate batch are split over the ranks (dataset replicated); call the
+    scorer with the SAME batch on every rank, e.g. after ``all_gather_batches``."""
+    import torch.distributed as dist
+    uid = broadcast_unique_id(group)
+    scorer.init_family_sharding(dist.get_rank(group), dist.get_world_size(group), uid)
+
+
+def all_gather_batches(local_adj, group=None):
+    """Concatenate every rank's CUDA adjacency batch ``[B, n, n]`` (same B everywhere) in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local_adj.shape[0],) + tuple(local_adj.shape[1:]), dtype=local_adj.dtype, device=local_adj.device)
+    dist.all_gather_into_tensor(out, local_adj.contiguous(), group=group)
+    return out

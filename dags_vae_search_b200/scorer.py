@@ -313,5 +313,11 @@ class BicScorer:
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self._lib.bic_comm_init(self._ctx, ctypes.addressof(buf), int(rank), int(world)))
 
+    def init_family_sharding(self, rank: int, world: int, unique_id: bytes) -> None:
+        """Dataset replicated, every rank is given the same global candidate batch; each rank counts
+        only the families it owns and the terms are all-reduced (bit-identical to one GPU)."""
+        self.init_row_sharding(rank, world, unique_id)
+        self._check(self._lib.bic_comm_mode(self._ctx, 1))
+
     def end_row_sharding(self) -> None:
         self._check(self._lib.bic_comm_destroy(self._ctx))

@@ -173,6 +173,14 @@ int bic_profile_get(bic_ctx *ctx, bic_profile_t *out);
 int bic_comm_unique_id(uint8_t id_out[128]);
 int bic_comm_init(bic_ctx *ctx, const uint8_t id[128], int rank, int world);
 int bic_comm_destroy(bic_ctx *ctx);
+/* What the communicator is used for.  BIC_SHARD_ROWS (default): each rank holds a slice of the
+ * rows, count tables are all-reduced (above).  BIC_SHARD_FAMILIES: every rank holds the whole
+ * dataset and is given the SAME (global) candidate batch; the batch is deduplicated identically
+ * everywhere, each rank counts only the families whose donor tree it owns, and the family terms
+ * are combined with ncclAllReduce(double, sum) — every other rank contributes exact zeros, so
+ * the scores are bit-identical to a single-GPU run.  Clears the cache. */
+enum { BIC_SHARD_ROWS = 0, BIC_SHARD_FAMILIES = 1 };
+int bic_comm_mode(bic_ctx *ctx, int mode);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,33 @@ def main():
     gathered = bdist.gather_scores(mine, len(dags))
     assert (np.abs(gathered - want) / np.abs(want)).max() < 1e-9
     full.close()
+
+    # ---- family sharding over a global batch (dataset replicated, derive path on: N >= 2^20)
+    N2 = 1_100_000
+    codes2 = synth.forward_sample(adj, card, cpts, N2, np.random.default_rng(5))
+    single = pkg.BicScorer(codes2, card, device=local)
+    want_bits = single.score_adjacency(dags)
+    single.close()
+    fam = pkg.BicScorer(codes2, card, device=local)
+    bdist.init_family_sharding(fam)
+    mine_cuda = torch.from_numpy(dags[blo:bhi] if (bhi - blo) * world == len(dags) else dags[:len(dags) // world]).cuda()
+    if (bhi - blo) * world == len(dags):
+        glob = bdist.all_gather_batches(mine_cuda)
+        assert np.array_equal(glob.cpu().numpy(), dags)
+    fam.profile_reset()
+    got_f = fam.score_adjacency(dags)
+    assert np.array_equal(got_f, want_bits)                 # bit-identical to one GPU
+    prof = fam.profile()
+    counted = torch.tensor([prof["families_counted"], prof["families_derived"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(counted)
+    st = fam.cache_stats()
+    assert int(counted.sum()) == st["families"] and prof["families_counted"] < st["families"]   # the work was split
+    got_f2 = fam.score_adjacency(dags2)                     # second batch: cached + new families
+    one = pkg.BicScorer(codes2, card, device=local)
+    one.score_adjacency(dags)
+    assert np.array_equal(got_f2, one.score_adjacency(dags2))
+    one.close()
+    fam.close()
     dist.barrier()
     if rank == 0:
         print("multigpu ok", world)
