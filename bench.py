@@ -195,16 +195,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Every core this process may run on.  Passed to the oracle explicitly: torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise make the 'all host cores' baseline single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(codes_host, card, adj_batch, target_seconds=12.0):
     """DAGs/s of the CPU restatement (no family cache, like the reference) on a bounded sample."""
     from oracle import c_oracle as C
-    threads = C.max_threads()
+    threads = host_threads()
     t0 = time.perf_counter()
-    C.score_dags_adj(codes_host, card, adj_batch[:2])
+    C.score_dags_adj(codes_host, card, adj_batch[:2], nthreads=threads)
     per_dag = (time.perf_counter() - t0) / 2
     sample = int(max(2, min(len(adj_batch), target_seconds / max(per_dag, 1e-9))))
     t0 = time.perf_counter()
-    C.score_dags_adj(codes_host, card, adj_batch[:sample])
+    C.score_dags_adj(codes_host, card, adj_batch[:sample], nthreads=threads)
     dt = time.perf_counter() - t0
     return sample / dt, threads, sample, dt
 
@@ -225,10 +234,10 @@ def run_reference(args, cfg, rows, batch):
         del codes_t
     except Exception:
         _, card, codes = make_dataset_cpu(cfg, rows)
-    threads = C.max_threads()
+    threads = host_threads()
     adj0 = candidate_batch(cfg, batch, 0, 0, 1)
     t0 = time.perf_counter()
-    C.score_dags_adj(codes, card, adj0[:2])
+    C.score_dags_adj(codes, card, adj0[:2], nthreads=threads)
     per_dag = (time.perf_counter() - t0) / 2
     total_steps = args.steps + args.warmup
     sample = int(max(1, min(batch, (150.0 / total_steps) / max(per_dag, 1e-9))))
@@ -236,7 +245,7 @@ def run_reference(args, cfg, rows, batch):
     for step in range(total_steps):
         adj = candidate_batch(cfg, batch, step, 0, 1)[:sample]
         t0 = time.perf_counter()
-        C.score_dags_adj(codes, card, adj)
+        C.score_dags_adj(codes, card, adj, nthreads=threads)
         if step >= args.warmup:
             times.append(time.perf_counter() - t0)
     value = sample * len(times) / sum(times)
