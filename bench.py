@@ -208,9 +208,10 @@ def cpu_oracle_rate(codes_host, card, adj_batch, target_seconds=12.0):
     """DAGs/s of the CPU restatement (no family cache, like the reference) on a bounded sample."""
     from oracle import c_oracle as C
     threads = host_threads()
-    t0 = time.perf_counter()
-    C.score_dags_adj(codes_host, card, adj_batch[:2], nthreads=threads)
-    per_dag = (time.perf_counter() - t0) / 2
+    for _ in range(3):   # the OpenMP pool needs a call or two to reach full speed after a thread-count change
+        t0 = time.perf_counter()
+        C.score_dags_adj(codes_host, card, adj_batch[:2], nthreads=threads)
+        per_dag = (time.perf_counter() - t0) / 2
     sample = int(max(2, min(len(adj_batch), target_seconds / max(per_dag, 1e-9))))
     t0 = time.perf_counter()
     C.score_dags_adj(codes_host, card, adj_batch[:sample], nthreads=threads)
@@ -236,9 +237,10 @@ def run_reference(args, cfg, rows, batch):
         _, card, codes = make_dataset_cpu(cfg, rows)
     threads = host_threads()
     adj0 = candidate_batch(cfg, batch, 0, 0, 1)
-    t0 = time.perf_counter()
-    C.score_dags_adj(codes, card, adj0[:2], nthreads=threads)
-    per_dag = (time.perf_counter() - t0) / 2
+    for _ in range(3):   # the OpenMP pool needs a call or two to reach full speed after a thread-count change
+        t0 = time.perf_counter()
+        C.score_dags_adj(codes, card, adj0[:2], nthreads=threads)
+        per_dag = (time.perf_counter() - t0) / 2
     total_steps = args.steps + args.warmup
     sample = int(max(1, min(batch, (150.0 / total_steps) / max(per_dag, 1e-9))))
     times = []
