@@ -157,6 +157,14 @@ def candidate_batch(cfg, batch, step, rank, world):
                                seed=CAND_SEED + step * world + rank)
 
 
+def describe_candidates(cfg):
+    if "fixture" in cfg:
+        return "reference encoder_dataset corpus (tests/golden), same batch every step"
+    if cfg.get("row_sharded"):
+        return "true DAG + local-search neighbours (<= 3 edge moves each), fresh batch every step, CSR parent lists"
+    return f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step"
+
+
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -433,12 +441,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    if "fixture" in cfg:
-        cand_desc = "reference encoder_dataset corpus (tests/golden), same batch every step"
-    elif sharded:
-        cand_desc = "true DAG + local-search neighbours (<= 3 edge moves each), fresh batch every step, CSR parent lists"
-    else:
-        cand_desc = f"Erdos-Renyi m in [{cfg['m_lo']},{cfg['m_hi']}], in-degree <= {cfg['cand_indeg']}, fresh batch every step"
+    cand_desc = describe_candidates(cfg)
     dags = batch * (1 if sharded else world) * args.steps   # row-sharded ranks score the same DAGs together
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

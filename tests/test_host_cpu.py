@@ -194,3 +194,22 @@ def test_predictor_dataset_builder(tmp_path, golden_dir):
             return np.array([[float(graphs[0])]], dtype=np.float32), None
     rows = predictors.generate_predictor_graphs_batch(OneAtATime(), lambda g: float(g), [4, 5])
     assert [r["target"] for r in rows] == [4.0, 5.0] and rows[1]["vector"].tolist() == [5.0]
+
+
+def test_bench_workload_definitions():
+    """Every bench workload builds its candidates and its config text on the CPU (a typo here only
+    shows up on the GPU box otherwise)."""
+    import bench
+    assert bench.host_threads() >= 1
+    for name, cfg in bench.WORKLOADS.items():
+        assert isinstance(bench.describe_candidates(cfg), str)
+        small = 6 if not cfg.get("row_sharded") else 3
+        adj = bench.candidate_batch(cfg, small, 1, 0, 2)
+        assert adj.shape == (small, cfg["n"], cfg["n"]) and adj.dtype == np.uint8
+        assert all(O.is_acyclic(a) for a in adj[:3])
+    cfg = bench.WORKLOADS["asia"]
+    _, card, codes = bench.make_dataset_cpu(cfg, 20_000)
+    assert codes.shape == (8, 20_000) and codes.max() <= 1
+    # the re-sampled asia rows keep the marginals of the bundled data within sampling noise
+    base = pkg.load_dataset("asia")[0]
+    assert np.abs(codes.mean(axis=1) - base.mean(axis=1)).max() < 0.02
