@@ -4,6 +4,8 @@ Row sharding (BASELINE config 5): every rank holds a slice of the rows, partial 
 summed by ncclAllReduce(uint32) inside libbicgpu; counts must equal the oracle's on the full
 dataset bit for bit, scores within 1e-9 relative, and all ranks must hold identical bits.
 Candidate sharding (configs 1-4): dataset replicated, each rank scores its slice of the batch.
+Family sharding: dataset replicated, every rank is given the same global batch and counts only the
+families it owns; the all-reduced terms must reproduce a single-GPU run bit for bit.
 """
 import os
 import sys
