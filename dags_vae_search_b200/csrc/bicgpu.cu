@@ -84,7 +84,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 std::mutex g_nccl_mu;
-constexpr int NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // nccl.h: ncclDataType_t / ncclRedOp_t
+constexpr int NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;   // nccl.h: ncclDataType_t / ncclRedOp_t
 
 }  // namespace
 
@@ -94,7 +94,7 @@ struct bic_ctx {
     std::mutex mu;
     std::string err;
     int sm_count = 148;
-    size_t attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
+    size_t attr_smem[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
 
     // dataset
     uint8_t *data = nullptr;
@@ -128,12 +128,19 @@ struct bic_ctx {
         long long l2_window = 32ll << 20;      // BIC_L2_WINDOW_MB: dataset bytes of one row slice kept L2-resident
         u32 class0_words = CLASS0_WORDS;       // BIC_CLASS0_WORDS: shared-memory words of a class-0 CTA
         int class0_threads = 256;              // BIC_CLASS0_THREADS: 256, 512 or 1024
+        int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
+                                               //   are counted in passes (0: always straight into HBM with L2 atomics)
+        int class2_threads = 1024;             // BIC_CLASS2_THREADS: 512 or 1024 (classes 2 and 3-in-passes: one CTA per SM)
+        bool slice_model = true;               // BIC_SLICE_MODEL=0: always cut the rows into L2 windows (round-1 versions a-h)
         void from_env() {
             if (const char *e = getenv("BIC_NO_DERIVE")) derive = atoi(e) == 0;
             if (const char *e = getenv("BIC_NO_PACK2")) pack2 = atoi(e) == 0;
             if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
             if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
             if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
+            if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
+            if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
+            if (const char *e = getenv("BIC_SLICE_MODEL")) slice_model = atoi(e) != 0;
             if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) class0_threads = t; }
         }
     } tune;
@@ -268,14 +275,14 @@ int header_fetch(bic_ctx *c) {
 
 // Dynamic shared memory above 48 KB needs a per-device opt-in on the kernel; the largest size set
 // so far is remembered per context (= per device) and per template instance.
-template <int THREADS, bool GLOBAL>
+template <int THREADS, bool GLOBAL, bool RANGE = false>
 int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
-    size_t &attr_smem = c->attr_smem[(THREADS == 128 ? 6 : THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
+    size_t &attr_smem = c->attr_smem[RANGE ? (THREADS == 512 ? 7 : 8) : (THREADS == 128 ? 6 : THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
     if (smem > 40 * 1024 && smem > attr_smem) {   // static + dynamic over 48 KB needs the opt-in
-        CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL, RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    k_count<THREADS, GLOBAL><<<(unsigned)items, THREADS, smem, c->stream>>>(a); LAUNCH(c);
+    k_count<THREADS, GLOBAL, RANGE><<<(unsigned)items, THREADS, smem, c->stream>>>(a); LAUNCH(c);
     CU(cudaGetLastError());
     ++c->prof.count_launches;
     return BIC_OK;
@@ -311,20 +318,56 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     const bool all_tables = want_tables || sharded || n_derived > 0;
 
     // Row slices per family.  Two reasons to slice: (a) few families -> enough CTAs to fill the
-    // GPU; (b) a dataset larger than L2 -> items run slice-major, so all resident CTAs sweep the
-    // same window of rows (all n columns of one slice <= L2_WINDOW bytes) and each column
-    // segment comes from HBM once per launch instead of once per family.  Never under 64K rows.
+    // GPU (two waves of the CTAs a class keeps resident per SM); (b) a dataset larger than L2 ->
+    // items run slice-major, so all resident CTAs sweep the same window of rows (all n columns of
+    // one slice <= L2_WINDOW bytes) and each column segment comes from HBM once per launch
+    // instead of once per family.  (b) has a price: every slice merges its shared-memory table
+    // into HBM with one L2 atomic per non-zero cell, so it is taken only when the HBM traffic it
+    // saves (the class's algorithmic row bytes beyond one pass over the dataset) outweighs those
+    // merges — with 5 GB of rows and a few dozen large-table families (diabetes-shaped local
+    // moves) 160 windows cost 3x the counting itself.  Never under 64K rows per slice.
     NeedArgs na;
     na.all = all_tables ? 1 : 0;
-    const long long target = (long long)c->sm_count * 8;
     const long long smax = std::max<long long>(1, c->N / 65536);
     const long long L2_WINDOW = c->tune.l2_window;
     const long long s_l2 = ((long long)c->n * c->N + L2_WINDOW - 1) / L2_WINDOW;
+    // measured on B200 (profiles/): streaming loads, L2 atomics, rows per second one CTA of a class counts
+    const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9;
+    const long long resident[NCLASS] = {4, 2, 1, 4};          // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
+    // class 3 in passes over shared-memory sub-ranges (k_count<512, false, true>) when every table
+    // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
+    const u32 span = CLASS2_CELLS;
+    const int P3 = (int)((h.max_cells + span - 1) / span);
+    const bool ranged = h.class_count[3] && c->tune.range_passes > 0 && P3 <= c->tune.range_passes &&
+                        c->N >= 4ll * (long long)h.max_cells;
     bool any_table = all_tables;
     for (int k = 0; k < NCLASS; ++k) {
-        long long cnt = h.class_count[k];
-        long long S = cnt ? std::min(smax, std::max(s_l2, (target + cnt - 1) / cnt)) : 1;
-        na.S[k] = (int)std::max<long long>(1, S);
+        const long long cnt = h.class_count[k];
+        long long S = 1;
+        if (cnt) {
+            // (a): slices that minimise waves x rows per item + merge traffic (whole waves matter
+            // when a class keeps one CTA per SM: 297 items on 148 SMs take three rounds, not two)
+            const bool rng3 = k == 3 && ranged;
+            const long long ctas = cnt * (rng3 ? P3 : 1);
+            const long long slots = (long long)c->sm_count * (rng3 ? 1 : resident[k]);
+            const long long hi = std::min(rng3 ? std::min(smax, c->N / (4ll * (long long)h.max_cells)) : smax,
+                                          std::max<long long>(1, 4 * slots / ctas));
+            const double merge1 = (k == 3 && !ranged) ? 0.0 : (double)h.class_cells[k] / RED_PER_S;
+            double best = 0.0;
+            for (long long s = 1; s <= hi; ++s) {
+                const double waves = (double)((ctas * s + slots - 1) / slots);
+                const double t = waves * ((double)c->N / (double)s) / CTA_ROWS_PER_S + (s > 1 || all_tables ? (double)s * merge1 : 0.0);
+                if (s == 1 || t < best * 0.97) { best = t; S = s; }
+            }
+            if (!c->tune.slice_model) S = std::min(smax, ((long long)c->sm_count * 8 + cnt - 1) / cnt);
+            // (b): L2 windows
+            if (s_l2 > S && !rng3) {
+                const double row_bytes = (double)h.alg_bytes[k] - 4.0 * (double)h.class_cells[k];
+                const double saved = (row_bytes - (double)c->n * (double)c->N) / HBM_BPS;
+                if (!c->tune.slice_model || saved > (double)(s_l2 - S) * merge1) S = s_l2;
+            }
+        }
+        na.S[k] = (int)std::max<long long>(1, std::min(smax, S));
         if (cnt && (na.S[k] > 1 || k == 3)) any_table = true;
     }
 
@@ -365,7 +408,9 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         a.jobs = c->class_jobs.as<int>() + (long long)k * max_jobs;
         a.S = na.S[k];
         a.njobs = (int)cnt;
-        long long items = cnt * a.S;
+        a.P = (k == 3 && ranged) ? P3 : 1;
+        a.span = span;
+        long long items = cnt * a.S * a.P;
         if (items > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
         bic_ctx::EvPair ev = {nullptr, nullptr, k};
         if (c->prof_on) {   // CUDA events on the launching stream, one pair per count launch
@@ -392,8 +437,12 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32))));
-        if (k == 2) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
-        if (k == 3) TRY((launch_count<256, true>(c, a, items, 0)));
+        const bool wide = c->tune.class2_threads == 1024;
+        if (k == 2 && !wide) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
+        if (k == 2 && wide) TRY((launch_count<1024, false>(c, a, items, cap[2] * sizeof(u32))));
+        if (k == 3 && !ranged) TRY((launch_count<256, true>(c, a, items, 0)));
+        if (k == 3 && ranged && !wide) TRY((launch_count<512, false, true>(c, a, items, span * sizeof(u32))));
+        if (k == 3 && ranged && wide) TRY((launch_count<1024, false, true>(c, a, items, span * sizeof(u32))));
         if (c->prof_on) {
             CU(cudaEventRecord(ev.b, c->stream));
             c->ev_used.push_back(ev);
@@ -438,6 +487,7 @@ int check_header_err(bic_ctx *c) {
 
 // keys of T instances sit in c->keybuf: look them up, insert + count the unseen families.
 int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
+    const bool famshard = c->comm != nullptr && c->comm_mode == BIC_SHARD_FAMILIES && c->world > 1;
     TRY(cache_ensure(c, T));
     CU(c->inst.ensure((size_t)T * sizeof(int)));
     CU(c->flag.ensure((size_t)T * sizeof(u32)));
@@ -456,11 +506,16 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     CU(c->donor_best.ensure((size_t)T * sizeof(u64)));   // (joint cells, index) of the cheapest donor announced so far
     CU(c->derived_list.ensure((size_t)T * sizeof(int)));
     const int derive = (c->tune.derive && !no_derive && c->N >= c->tune.derive_min_rows) ? 1 : 0;
-    const bool famshard = c->comm != nullptr && c->comm_mode == BIC_SHARD_FAMILIES && c->world > 1;
     if (derive) {
+        const int aw = famshard ? c->world : 1;
         CU(cudaMemsetAsync(c->donor_best.p, 0xff, (size_t)T * sizeof(u64), c->stream));
-        k_announce<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table, (u32)(c->table_cap - 1),
-                                             c->d_card, c->donor_best.as<u64>()); LAUNCH(c);
+        k_announce<<<nblk((T + aw - 1) / aw, 256), 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table,
+                                                                       (u32)(c->table_cap - 1), c->d_card, c->donor_best.as<u64>(),
+                                                                       famshard ? c->rank_id : 0, aw); LAUNCH(c);
+        if (famshard) {   // every rank announced for 1/world of the donors: combine the minima
+            int e = g_nccl.AllReduce(c->donor_best.p, c->donor_best.p, (size_t)T, NCCL_UINT64, NCCL_MIN, c->comm, c->stream);
+            if (e != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(donor search) failed");
+        }
     }
     if (derive) { k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c); }
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,

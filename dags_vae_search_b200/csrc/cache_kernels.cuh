@@ -303,6 +303,8 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
     u32 pos = atomicAdd(&hdr->class_count[cls], 1u);
     class_jobs[(long long)cls * max_jobs + pos] = (int)j;
     atomicAdd(&hdr->alg_bytes[cls], (u64)(k + 1) * (u64)N + 4ull * cells);
+    atomicAdd(&hdr->class_cells[cls], cells);
+    atomicMax(&hdr->max_cells, (u32)cells);
 }
 
 // Owners of PENDING entries take id = base + rank, publish their key in the registry and
@@ -363,9 +365,12 @@ __device__ __forceinline__ void announce_to(const u64 *sub, int W64, u64 pack, l
     }
 }
 
+// world > 1 (family sharding): rank r announces only for the donors g = r, r + world, ...; the
+// per-rank minima are then combined with ncclAllReduce(uint64, min).
 __global__ void k_announce(const u64 *__restrict__ regkeys, int W64, long long base, const Header *hdr,
-                           const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, u64 *best) {
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                           const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, u64 *best,
+                           int rank, int world) {
+    long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * world + rank;
     if (g >= hdr->f_new) return;
     int Wk = W64 + 1;
     const u64 *mine = regkeys + (base + g) * Wk;

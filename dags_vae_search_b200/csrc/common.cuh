@@ -32,8 +32,9 @@ struct Header {
     u32 class_count[NCLASS];   // of those, per count-kernel class
     u32 err;                   // bit 0: q*r over MAX_CELLS; bit 1: bad parent index
     u32 n_invalid;             // DAGs rejected (cyclic, self loop, labels not a permutation)
-    u32 pad;
+    u32 max_cells;             // largest count table among the new families
     u64 alg_bytes[NCLASS];     // sum (k+1)*N + 4*q*r over the new families, per class
+    u64 class_cells[NCLASS];   // sum q*r over the new families, per class (what a slice merges into HBM)
     u64 table_cells;           // cells of all count tables that must live in HBM (scan total)
     u64 cells_all;             // cells of every described family: upper bound of table_cells, exact when all tables live in HBM
     u32 n_derived;             // new families whose table is marginalised from a counted superset

@@ -28,6 +28,8 @@ struct CountArgs {
     const int *jobs;         // job ids of this launch (one class)
     int njobs;               // how many
     int S;                   // row slices per family
+    int P;                   // RANGE kernel: cell sub-range passes per (family, slice) at most
+    u32 span;                // RANGE kernel: cells of one sub-range (the shared-memory table of a CTA)
     u32 cap_words;           // shared-memory words available to one CTA's table(s)
     u32 *arena;              // HBM count tables
     const u32 *need;         // per job: cells if its table lives in HBM, else 0 (nullable)
@@ -47,6 +49,7 @@ struct FamMeta {
     int small;  // every column of the family has <= 4 states (2-bit packed copy usable)
     u32 R;      // lane replicas of the shared-memory table (power of two, <= 32)
     u32 mul;    // byte offset of a cell = cell * mul  (mul = 4 * R)
+    u32 lo4, span4;   // RANGE kernel: byte offset of the CTA's first cell, bytes of its sub-range
     int par[KMAX];
     u32 rad[KMAX];
 };
@@ -110,10 +113,20 @@ __device__ __forceinline__ void bump_off(u32 *hist, u32 byte_off) {
     atomicAdd(reinterpret_cast<u32 *>(reinterpret_cast<char *>(hist) + byte_off), 1u);   // ATOMS.POPC.INC / RED
 }
 
-// byte offsets of the 16 rows of a group, in row order; rows >= N are skipped
-template <bool GLOBAL>
-__device__ __forceinline__ void bump16(u32 *hist, const u32 (&off)[16], long long row0, long long N) {
-    if (row0 + 16 <= N) {
+// byte offsets of the 16 rows of a group, in row order; rows >= N are skipped.  RANGE: the CTA
+// owns the cells [lo4, lo4 + span4) (byte offsets) of a table too large for shared memory and
+// ignores the rows that fall outside (another pass counts them).
+template <bool GLOBAL, bool RANGE = false>
+__device__ __forceinline__ void bump16(u32 *hist, const u32 (&off)[16], long long row0, long long N, u32 lo4 = 0,
+                                       u32 span4 = 0) {
+    if (RANGE) {
+        const int nv = row0 + 16 <= N ? 16 : (int)(N - row0);
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const u32 d = off[b] - lo4;
+            if (b < nv && d < span4) bump_off<false>(hist, d);
+        }
+    } else if (row0 + 16 <= N) {
 #pragma unroll
         for (int b = 0; b < 16; ++b) bump_off<GLOBAL>(hist, off[b]);
     } else {
@@ -184,7 +197,7 @@ __device__ __forceinline__ void cells_u32(const uint4 (&w)[K + 1], const u32 (&r
 
 // K parents known at compile time: all K+1 column loads of a row group are issued before any
 // is consumed (K+1 independent 16-byte loads in flight per thread).
-template <int K, int MODE, bool GLOBAL, int THREADS>
+template <int K, int MODE, bool GLOBAL, int THREADS, bool RANGE = false>
 __device__ __forceinline__ void count_rows_k(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
                                              long long N, long long v0, long long v1, u32 *hist) {
     const uint8_t *cp[K + 1];
@@ -205,15 +218,15 @@ __device__ __forceinline__ void count_rows_k(const FamMeta &m, const uint8_t *__
         if (MODE == MODE_U8) cells_u8<K>(w, rad, mul, off);
         else if (MODE == MODE_U16) cells_u16<K>(w, rad, mul, off);
         else cells_u32<K>(w, rad, mul, off);
-        bump16<GLOBAL>(hist, off, v * 16, N);
+        bump16<GLOBAL, RANGE>(hist, off, v * 16, N, m.lo4, m.span4);
     }
 }
 
-template <int K, bool GLOBAL, int THREADS>
+template <int K, bool GLOBAL, int THREADS, bool RANGE = false>
 __device__ __forceinline__ void count_rows_mode(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
                                                 long long N, long long v0, long long v1, u32 *hist) {
-    if (GLOBAL) {   // class 3 tables are far above the packed-lane limits
-        count_rows_k<K, MODE_U32, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist);
+    if (GLOBAL || RANGE) {   // class 3 tables are far above the packed-lane limits
+        count_rows_k<K, MODE_U32, GLOBAL, THREADS, RANGE>(m, data, stride, N, v0, v1, hist);
         return;
     }
     switch (count_mode(m.cells, m.R)) {
@@ -302,7 +315,7 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
 }
 
 // Any number of parents (k > 6): columns are walked one at a time.
-template <bool GLOBAL, int THREADS>
+template <bool GLOBAL, int THREADS, bool RANGE = false>
 __device__ __forceinline__ void count_rows_any(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
                                                long long N, long long v0, long long v1, u32 *hist) {
     const uint8_t *child = data + (long long)m.node * stride;
@@ -321,7 +334,7 @@ __device__ __forceinline__ void count_rows_any(const FamMeta &m, const uint8_t *
         }
 #pragma unroll
         for (int b = 0; b < 16; ++b) off[b] *= m.mul;
-        bump16<GLOBAL>(hist, off, v * 16, N);
+        bump16<GLOBAL, RANGE>(hist, off, v * 16, N, m.lo4, m.span4);
     }
 }
 
@@ -422,8 +435,15 @@ __device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab
     return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh);
 }
 
-template <int THREADS, bool GLOBAL>
+// RANGE (class 3 when the rows dwarf the table): the table does not fit one CTA's shared memory,
+// so a (family, slice) is counted in P passes; pass p keeps cells [p * span, (p + 1) * span) in
+// shared memory, streams the slice and skips the rows whose cell lies elsewhere.  The passes of a
+// slice are neighbours in the grid, so all but the first read the rows from L2.  That trades
+// P x the streaming for shared-memory atomics instead of one L2 atomic per row (measured
+// 0.09-0.19 T/s for the whole GPU).
+template <int THREADS, bool GLOBAL, bool RANGE = false>
 __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
+    static_assert(!(GLOBAL && RANGE), "a sub-range table lives in shared memory");
     extern __shared__ u32 s_hist[];
     __shared__ FamMeta m;
     __shared__ double s_red[32];
@@ -431,12 +451,18 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
 
     // slice-major item order: the CTAs resident at any moment work on the same row window of
     // the dataset, which the host sizes to stay L2-resident
-    const int slice = blockIdx.x / a.njobs;
-    const int j = a.jobs[blockIdx.x - slice * a.njobs];
+    const int per_slice = RANGE ? a.njobs * a.P : a.njobs;
+    const int slice = blockIdx.x / per_slice;
+    const int in_slice = blockIdx.x - slice * per_slice;
+    const int pass = RANGE ? in_slice / a.njobs : 0;
+    const int j = a.jobs[in_slice - pass * a.njobs];
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
 
     const u32 cells = m.cells;
+    const u32 lo = RANGE ? (u32)pass * a.span : 0u;
+    if (RANGE && lo >= cells) return;   // this family needs fewer passes than the largest of the launch
+    const u32 span = RANGE ? min(a.span, cells - lo) : cells;
     // slice boundaries on multiples of 8 vectors (128 bytes): a warp's 512-byte load then covers
     // exactly 4 cache lines (ncu showed 5.2 data-pipe wavefronts per load with unaligned slices)
     const long long nvec = (a.N + 15) >> 4;
@@ -451,7 +477,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         // at least 16 rows per replicated counter
         u32 R = 1;
         const long long rows_here = (v1 - v0) * 16;
-        if (!GLOBAL)
+        if (!GLOBAL && !RANGE)
             while (R < 32 && cells * (R * 2) <= a.cap_words && cells * (R * 2) <= 16383u &&   // 16-bit lane offsets
                    cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) && (long long)cells * (R * 2) * 16 <= rows_here)
                 R *= 2;
@@ -461,20 +487,22 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         if (R < 16) R = 1;
         m.R = R;
         m.mul = 4u * R;
+        m.lo4 = lo * 4u;
+        m.span4 = span * 4u;
     }
     __syncthreads();
     const u32 R = m.R;
     u32 *tab = (a.need && a.need[j]) ? a.arena + a.table_off[j] : nullptr;
     u32 *hist = GLOBAL ? tab : s_hist + (threadIdx.x & (R - 1));
     if (!GLOBAL) {
-        for (u32 c = threadIdx.x; c < cells * R; c += THREADS) s_hist[c] = 0;
+        for (u32 c = threadIdx.x; c < span * R; c += THREADS) s_hist[c] = 0;
         __syncthreads();
     }
 
     // packed path: all columns <= 4 states, index * mul fits 16-bit lanes.  The choice must not
     // depend on the slice (the two paths cut the rows into slices differently), hence no R here:
     // R > 1 implies cells * R <= 16383 (replica selection above).
-    const bool packed = !GLOBAL && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
+    const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
         switch (m.k) {
             case 0: count_rows_p2<0, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
@@ -487,33 +515,34 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         }
     } else
     switch (m.k) {
-        case 0: count_rows_mode<0, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 1: count_rows_mode<1, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 2: count_rows_mode<2, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 3: count_rows_mode<3, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 4: count_rows_mode<4, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 5: count_rows_mode<5, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 6: count_rows_mode<6, GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        default: count_rows_any<GLOBAL, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 0: count_rows_mode<0, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 1: count_rows_mode<1, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 2: count_rows_mode<2, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 3: count_rows_mode<3, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 4: count_rows_mode<4, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 5: count_rows_mode<5, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 6: count_rows_mode<6, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        default: count_rows_any<GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
     }
     __syncthreads();
-    if (!GLOBAL && R > 1) compact_replicas<THREADS>(s_hist, cells, R);
+    if (!GLOBAL && !RANGE && R > 1) compact_replicas<THREADS>(s_hist, cells, R);
 
     if (!GLOBAL && tab) {   // merge this slice's shared-memory table into the HBM table
-        for (u32 c = threadIdx.x; c < cells; c += THREADS) {
+        for (u32 c = threadIdx.x; c < span; c += THREADS) {
             u32 v = s_hist[c];
-            if (v) atomicAdd(tab + c, v);
+            if (v) atomicAdd(tab + lo + c, v);
         }
     }
     if (!a.reduce) return;
 
     double ll;
-    if (!GLOBAL && a.S == 1) {
+    if (!GLOBAL && !RANGE && a.S == 1) {
         ll = family_term<false>(a, s_hist, m, s_red);
     } else {
+        const u32 parts = RANGE ? (u32)a.S * ((cells + a.span - 1) / a.span) : (u32)a.S;
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(a.done + j, 1u) == (u32)(a.S - 1));
+        if (threadIdx.x == 0) s_last = (atomicAdd(a.done + j, 1u) == parts - 1);
         __syncthreads();
         if (!s_last) return;
         __threadfence();

@@ -151,8 +151,9 @@ typedef struct {
     int64_t rows_counted;  /* sum over counted families of N (this rank's rows)             */
     int64_t alg_bytes;     /* sum over counted families of (k+1)*N + 4*q*r                  */
     /* the same, split by count-kernel class (0..2: shared-memory tables of <= 2048 / 12288 /
-     * 49152 cells, kernels k_count<256,false> / <512,false> / <512,false>; 3: HBM tables,
-     * k_count<256,true>) */
+     * 49152 cells, kernels k_count<256,false> / <512,false> / <512,false>; 3: larger tables,
+     * counted in passes over shared-memory sub-ranges, k_count<512,false,true>, when the rows
+     * dwarf the table, else straight into HBM with L2 atomics, k_count<256,true>) */
     double class_ms[4];
     int64_t class_launches[4];
     int64_t class_families[4];

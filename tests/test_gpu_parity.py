@@ -435,6 +435,58 @@ def test_packed_and_byte_paths_agree(monkeypatch):
     assert_scores(packed[:30], C.score_dags_adj(codes, card, dags[:30]))
 
 
+# ----------------------------------- tables above one CTA's shared memory (class 3), slicing
+def test_class3_subrange_passes_match_oracle_and_l2_atomics(monkeypatch):
+    """Tables of more than 49152 cells: when the rows dwarf the table it is counted in passes over
+    shared-memory sub-ranges (k_count<512,false,true>), otherwise straight into HBM with L2
+    atomics.  Both must give the oracle's counts and identical score bits; ragged row count,
+    k <= 6 (specialised row loop) and k > 6 (generic loop), one and several row slices."""
+    N = 1_200_003
+    rng = np.random.default_rng(77)
+    card = np.array([21, 20, 19, 5, 7] + [3] * 11, dtype=np.int32)
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    codes[3] = (codes[0] + codes[4]) % 5                      # structure: not every cell is hit equally
+    fams = [(4, [0, 1, 2]),                                   # 55 860 cells: 2 passes
+            (0, [1, 2, 3, 4]),                                # 279 300 cells: 6 passes
+            (5, list(range(6, 16))),                          # 3^11 = 177 147 cells, k = 10
+            (3, [0, 1, 2])]                                   # 39 900 cells: class 2, same launch sequence
+    node, off, par = csr_of(fams)
+    with pkg.BicScorer(codes, card) as s:
+        s.profile_reset()
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for (i, ps), t in zip(fams, tabs):
+            assert t.sum() == N
+            assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (i, ps)
+        ranged = s.score_families_csr(node, off, par, no_cache=True)
+        one = s.score_families([4], [[0, 1, 2]], no_cache=True)          # alone: several row slices
+        assert one[0] == ranged[0]
+        assert np.array_equal(s.family_counts(4, [0, 1, 2]), tabs[0])
+    assert_scores(ranged, C.score_families(codes, card, node, off, par))
+    monkeypatch.setenv("BIC_RANGE_PASSES", "0")
+    with pkg.BicScorer(codes, card) as s:
+        tabs0 = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for t, t0 in zip(tabs, tabs0):
+            assert np.array_equal(t, t0)
+        assert np.array_equal(s.score_families_csr(node, off, par, no_cache=True), ranged)
+
+
+def test_slice_choice_does_not_change_bits(monkeypatch):
+    """The number of row slices per family is a cost decision (L2 windows vs merge traffic);
+    counts are integer sums and the fp64 reduce has a fixed order, so any choice gives the same
+    bits."""
+    N = 1_300_000
+    adj, card, cpts = synth.make_network(40, 60, 3, [2, 3, 5, 9], seed=51)
+    codes = synth.forward_sample(adj, card, cpts, N, np.random.default_rng(52))     # 52 MB: two L2 windows
+    dags = synth.er_candidates(40, 6, 39, 70, 4, seed=53)
+    with pkg.BicScorer(codes, card) as s:
+        a = s.score_adjacency(dags, no_cache=True)
+    monkeypatch.setenv("BIC_SLICE_MODEL", "0")
+    with pkg.BicScorer(codes, card) as s:
+        b = s.score_adjacency(dags, no_cache=True)
+    assert np.array_equal(a, b)
+    assert_scores(a[:2], C.score_dags_adj(codes, card, dags[:2]))
+
+
 # ------------------------------------------------------- sub-batching, cache growth, misc API
 def test_large_batch_spans_sub_batches(asia, asia_scorer):
     """600k DAGs x 8 nodes = 4.8 M instances > the 4 M-instance sub-batch: two passes through the
