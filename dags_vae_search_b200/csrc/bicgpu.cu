@@ -117,7 +117,7 @@ struct bic_ctx {
 
     // per-sub-batch workspace
     DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
-    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_best, derived_list;
+    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_best, derived_list, derived_sorted;
     // Tuning knobs.  Defaults are the values swept on B200; the BIC_*
     // environment variables exist for those sweeps and for tests, not as a supported interface.
     struct Tuning {
@@ -313,6 +313,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     const Header &h = *c->h_hdr;
     const bool sharded = c->comm != nullptr && c->comm_mode == BIC_SHARD_ROWS;
     const u32 n_derived = with_donors ? h.n_derived : 0;
+    const u32 max_cells = h.max_cells;
     u32 lvl_count[DERIVE_LEVELS];
     for (int l = 0; l < DERIVE_LEVELS; ++l) lvl_count[l] = with_donors ? h.lvl_count[l] : 0;   // header is re-fetched below
     const bool all_tables = want_tables || sharded || n_derived > 0;
@@ -432,6 +433,8 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         const int c0t = c->tune.class0_threads;
         const u32 cap[NCLASS] = {c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
+        const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
+        a.stage_words = k == 3 ? (ranged ? span : GLOBAL_STAGE) : cap[k];
         if (k == 0 && c0t == 128) TRY((launch_count<128, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
@@ -440,7 +443,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         const bool wide = c->tune.class2_threads == 1024;
         if (k == 2 && !wide) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 2 && wide) TRY((launch_count<1024, false>(c, a, items, cap[2] * sizeof(u32))));
-        if (k == 3 && !ranged) TRY((launch_count<256, true>(c, a, items, 0)));
+        if (k == 3 && !ranged) TRY((launch_count<256, true>(c, a, items, GLOBAL_STAGE * sizeof(u32))));
         if (k == 3 && ranged && !wide) TRY((launch_count<512, false, true>(c, a, items, span * sizeof(u32))));
         if (k == 3 && ranged && wide) TRY((launch_count<1024, false, true>(c, a, items, span * sizeof(u32))));
         if (c->prof_on) {
@@ -468,9 +471,14 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         CU(cudaGetLastError());
     }
     if (n_derived) {   // tables of the counted families are complete: marginalise, most parents first
+        // chunks per family: one per 4096 donor cells, as many as the largest table of the batch can need
+        const int dch = (int)std::min<u32>(DERIVE_CHUNKS, std::max<u32>(1u, max_cells / 4096u));
+        long long first = 0;
         for (int l = DERIVE_LEVELS - 1; l >= 0; --l) {
             if (!lvl_count[l]) continue;
-            k_derive<256><<<n_derived, 256, 0, c->stream>>>(a, c->derived_list.as<int>(), l); LAUNCH(c);
+            k_derive<256><<<lvl_count[l] * dch, 256, 0, c->stream>>>(a, c->derived_sorted.as<int>() + first, dch,
+                                                                     c->cells_arr.as<u32>()); LAUNCH(c);
+            first += lvl_count[l];
         }
         CU(cudaGetLastError());
     }
@@ -505,11 +513,12 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     CU(c->donor.ensure((size_t)T * sizeof(int)));
     CU(c->donor_best.ensure((size_t)T * sizeof(u64)));   // (joint cells, index) of the cheapest donor announced so far
     CU(c->derived_list.ensure((size_t)T * sizeof(int)));
+    CU(c->derived_sorted.ensure((size_t)T * sizeof(int)));
     const int derive = (c->tune.derive && !no_derive && c->N >= c->tune.derive_min_rows) ? 1 : 0;
     if (derive) {
         const int aw = famshard ? c->world : 1;
         CU(cudaMemsetAsync(c->donor_best.p, 0xff, (size_t)T * sizeof(u64), c->stream));
-        k_announce<<<nblk((T + aw - 1) / aw, 256), 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table,
+        k_announce<<<nblk(((T + aw - 1) / aw) * 32, 256), 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table,
                                                                        (u32)(c->table_cap - 1), c->d_card, c->donor_best.as<u64>(),
                                                                        famshard ? c->rank_id : 0, aw); LAUNCH(c);
         if (famshard) {   // every rank announced for 1/world of the donors: combine the minima
@@ -521,6 +530,10 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
                                              derive ? c->donor.as<int>() : nullptr, c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
                                              c->derived_list.as<int>(), c->rank_id, famshard ? c->world : 1); LAUNCH(c);
+    if (derive) {
+        k_group_derived<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->derived_list.as<int>(),
+                                                  c->derived_sorted.as<int>()); LAUNCH(c);
+    }
     CU(cudaGetLastError());
     TRY(header_fetch(c));
     long long f_new = c->h_hdr->f_new;
@@ -649,7 +662,9 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
         if ((flags & BIC_FLAG_NO_CYCLE_CHECK) || fmt == FMT_WIRE) {
             k_count_bad<<<nblk(Bc, 256), 256, 0, c->stream>>>(c->dag_bad.as<uint8_t>(), Bc, c->d_hdr); LAUNCH(c);
         } else {
-            k_acyclic<<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
+            if (n > 128) k_acyclic<true><<<(unsigned)Bc, ACYC_WIDE_THREADS, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
+                                                                             c->dag_bad.as<uint8_t>(), c->d_hdr); 
+            else k_acyclic<false><<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
                                                                              c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
         }
         CU(cudaGetLastError());
@@ -660,8 +675,13 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
             CU(c->out_stage.ensure((size_t)Bc * sizeof(double)));
             d_out = c->out_stage.as<double>();
         }
-        k_gather_dags<<<nblk(Bc, 128), 128, 0, c->stream>>>(c->inst.as<int>(), c->table, Bc, n, c->dag_bad.as<uint8_t>(),
-                                                            c->reg_ll, c->reg_np, pen, d_out); LAUNCH(c);
+        if (n >= 64)
+            k_gather_dags_warp<<<nblk(Bc * 32, 128), 128, 0, c->stream>>>(c->inst.as<int>(), c->table, Bc, n, c->dag_bad.as<uint8_t>(),
+                                                                          c->reg_ll, c->reg_np, pen, d_out);
+        else
+            k_gather_dags<<<nblk(Bc, 128), 128, 0, c->stream>>>(c->inst.as<int>(), c->table, Bc, n, c->dag_bad.as<uint8_t>(),
+                                                                c->reg_ll, c->reg_np, pen, d_out);
+        LAUNCH(c);
         CU(cudaGetLastError());
         if (!dev) CU(cudaMemcpyAsync(out + b0, d_out, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         TRY(finish_call(c));

@@ -92,43 +92,51 @@ __global__ void k_keys_wire(const uint8_t *__restrict__ labels, const u32 *__res
 // ---------------------------------------------------------------------------- acyclic
 // One warp per DAG: peel parentless vertices (Kahn) on bitmasks held in shared memory.
 // dag_bad[b] in: self loop / bad index; out: also set when a cycle remains.
+// One warp per DAG, or (WIDE, networks of more than 128 variables) one 256-thread block per DAG so
+// that a peeling round tests at most four vertices per thread: 413 vertices on one warp cost
+// 150 us per launch, latency-bound.
 constexpr int ACYC_WARPS = 4;
-__global__ void __launch_bounds__(ACYC_WARPS * 32)
+constexpr int ACYC_WIDE_THREADS = 256;
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? ACYC_WIDE_THREADS : ACYC_WARPS * 32)
 k_acyclic(const u64 *__restrict__ keybuf, long long B, int n, int W64, uint8_t *dag_bad, Header *hdr) {
-    __shared__ u64 s_alive[ACYC_WARPS][W64MAX];
-    __shared__ u64 s_next[ACYC_WARPS][W64MAX];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long b = (long long)blockIdx.x * ACYC_WARPS + warp;
+    constexpr int GROUPS = WIDE ? 1 : ACYC_WARPS;
+    constexpr int LANES = WIDE ? ACYC_WIDE_THREADS : 32;
+    __shared__ u64 s_alive[GROUPS][W64MAX];
+    __shared__ u64 s_next[GROUPS][W64MAX];
+    const int grp = WIDE ? 0 : (int)(threadIdx.x >> 5), lane = WIDE ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    const long long b = (long long)blockIdx.x * GROUPS + grp;
     if (b >= B) return;
+    auto sync = [] { if (WIDE) __syncthreads(); else __syncwarp(); };
     int Wk = W64 + 1;
-    u64 *alive = s_alive[warp], *next = s_next[warp];
-    bool bad = dag_bad[b] != 0;
+    u64 *alive = s_alive[grp], *next = s_next[grp];
+    bool bad = dag_bad[b] != 0;        // uniform over the group
     if (!bad) {
-        for (int w = lane; w < W64; w += 32) {
+        for (int w = lane; w < W64; w += LANES) {
             int bits = min(64, n - w * 64);
             u64 m = (bits >= 64) ? ~0ull : ((1ull << bits) - 1ull);
             alive[w] = m;
             next[w] = m;
         }
-        __syncwarp();
+        sync();
         const u64 *keys = keybuf + b * (long long)n * Wk;
         while (true) {
-            for (int i = lane; i < n; i += 32) {
+            for (int i = lane; i < n; i += LANES) {
                 if (!((alive[i >> 6] >> (i & 63)) & 1ull)) continue;
                 const u64 *pm = keys + (long long)i * Wk + 1;
                 bool blocked = false;
                 for (int w = 0; w < W64; ++w) blocked = blocked || ((pm[w] & alive[w]) != 0);
                 if (!blocked) atomicAnd(&next[i >> 6], ~(1ull << (i & 63)));
             }
-            __syncwarp();
+            sync();
             bool changed = false, any = false;
             for (int w = 0; w < W64; ++w) {   // every lane reads the same words: uniform result
                 changed = changed || (next[w] != alive[w]);
                 any = any || (next[w] != 0);
             }
-            __syncwarp();
-            for (int w = lane; w < W64; w += 32) alive[w] = next[w];
-            __syncwarp();
+            sync();
+            for (int w = lane; w < W64; w += LANES) alive[w] = next[w];
+            sync();
             if (!any) break;
             if (!changed) { bad = true; break; }
         }
@@ -365,12 +373,14 @@ __device__ __forceinline__ void announce_to(const u64 *sub, int W64, u64 pack, l
     }
 }
 
-// world > 1 (family sharding): rank r announces only for the donors g = r, r + world, ...; the
-// per-rank minima are then combined with ncclAllReduce(uint64, min).
+// One warp per donor: the lanes share out its subsets (the probes are independent, the minimum
+// is order-free).  world > 1 (family sharding): rank r announces only for the donors g = r,
+// r + world, ...; the per-rank minima are then combined with ncclAllReduce(uint64, min).
 __global__ void k_announce(const u64 *__restrict__ regkeys, int W64, long long base, const Header *hdr,
                            const u32 *__restrict__ table, u32 mask, const int *__restrict__ card, u64 *best,
                            int rank, int world) {
-    long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * world + rank;
+    const int lane = threadIdx.x & 31;
+    long long g = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * world + rank;
     if (g >= hdr->f_new) return;
     int Wk = W64 + 1;
     const u64 *mine = regkeys + (base + g) * Wk;
@@ -395,14 +405,14 @@ __global__ void k_announce(const u64 *__restrict__ regkeys, int W64, long long b
     if (m < 2 || m > DERIVE_LEVELS) return;
     const u64 pack = (cells << 32) | (u64)g;
     if (m <= ANNOUNCE_MAX_VARS) {
-        for (u32 pick = 1; pick + 1 < (1u << m); ++pick) {   // every non-empty proper subset
+        for (u32 pick = 1 + lane; pick + 1 < (1u << m); pick += 32) {   // every non-empty proper subset
             for (int w = 0; w < W64; ++w) sub[w] = 0;
             for (int i = 0; i < m; ++i)
                 if (pick >> i & 1u) sub[vars[i] >> 6] |= 1ull << (vars[i] & 63);
             announce_to(sub, W64, pack, base, table, mask, regkeys, best);
         }
     } else {
-        for (int i = 0; i < m; ++i) {
+        for (int i = lane; i < m; i += 32) {
             for (int w = 0; w < W64; ++w) sub[w] = vset[w];
             sub[vars[i] >> 6] &= ~(1ull << (vars[i] & 63));
             announce_to(sub, W64, pack, base, table, mask, regkeys, best);
@@ -464,6 +474,21 @@ __global__ void k_describe_new(const u64 *__restrict__ regkeys, int W64, long lo
     atomicAdd(&hdr->lvl_count[pc], 1u);
 }
 
+// Group the derived families by level (number of parents), highest level first, so that each
+// k_derive launch gets exactly its own families.  Order inside a level does not matter.
+__global__ void k_group_derived(const u64 *__restrict__ regkeys, int W64, long long base, Header *hdr,
+                                const int *__restrict__ derived_list, int *derived_by_level) {
+    u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hdr->n_derived) return;
+    const int j = derived_list[idx];
+    const u64 *key = regkeys + (base + j) * (W64 + 1);
+    int pc = 0;
+    for (int w = 0; w < W64; ++w) pc += __popcll(key[1 + w]);
+    u32 start = 0;
+    for (int l = DERIVE_LEVELS - 1; l > pc; --l) start += hdr->lvl_count[l];
+    derived_by_level[start + atomicAdd(&hdr->lvl_cursor[pc], 1u)] = j;
+}
+
 // Cache-bypassing path (bic_count_families): every listed family is job t.
 __global__ void k_describe_direct(const u64 *__restrict__ keybuf, int W64, long long T,
                                   const int *__restrict__ card, long long N, u32 max_jobs, Header *hdr,
@@ -509,6 +534,28 @@ __global__ void k_gather_dags(const int *__restrict__ inst, const u32 *__restric
         s += ll[id] - pen * np[id];
     }
     out[b] = s;
+}
+
+// The same sum for wide networks (n >= 64): one warp per DAG.  The lanes fetch 32 terms at a time,
+// lane 0 adds them in variable order, so the bits equal the one-thread version's.
+__global__ void k_gather_dags_warp(const int *__restrict__ inst, const u32 *__restrict__ table, long long B, int n,
+                                   const uint8_t *__restrict__ dag_bad, const double *__restrict__ ll,
+                                   const double *__restrict__ np, double pen, double *out) {
+    const int lane = threadIdx.x & 31;
+    long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    if (dag_bad[b]) { if (lane == 0) out[b] = __longlong_as_double(0x7ff8000000000000LL); return; }
+    double s = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        double term = 0.0;
+        if (i0 + lane < n) {
+            long long id = resolve_id(inst[b * n + i0 + lane], table);
+            term = ll[id] - pen * np[id];
+        }
+        const int cnt = min(32, n - i0);
+        for (int k = 0; k < cnt; ++k) s += __shfl_sync(0xffffffffu, term, k);
+    }
+    if (lane == 0) out[b] = s;
 }
 
 __global__ void k_gather_fams(const int *__restrict__ inst, const u32 *__restrict__ table, long long T,

@@ -39,6 +39,7 @@ struct Header {
     u64 cells_all;             // cells of every described family: upper bound of table_cells, exact when all tables live in HBM
     u32 n_derived;             // new families whose table is marginalised from a counted superset
     u32 lvl_count[DERIVE_LEVELS];   // of those, by number of parents
+    u32 lvl_cursor[DERIVE_LEVELS];  // device scratch: fill positions while the derived families are grouped by level
 };
 
 __device__ __forceinline__ u64 mix64(u64 x) {

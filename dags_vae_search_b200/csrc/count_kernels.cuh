@@ -31,6 +31,7 @@ struct CountArgs {
     int P;                   // RANGE kernel: cell sub-range passes per (family, slice) at most
     u32 span;                // RANGE kernel: cells of one sub-range (the shared-memory table of a CTA)
     u32 cap_words;           // shared-memory words available to one CTA's table(s)
+    u32 stage_words;         // dynamic shared memory of the launch in words (staging buffer of the HBM-table reduce)
     u32 *arena;              // HBM count tables
     const u32 *need;         // per job: cells if its table lives in HBM, else 0 (nullable)
     const u64 *table_off;    // per job: offset into arena (valid where need != 0)
@@ -367,72 +368,113 @@ __device__ __forceinline__ void compact_replicas(u32 *hist, u32 cells, u32 R) {
 // (shuffle tree per warp, then the 8 warps in index order).  A family's log-likelihood is
 // therefore bit-identical for every kernel class, slice count and for the row-sharded path.
 constexpr int RED_LANES = 256;
+constexpr u32 STAGE_WORDS = 6144;   // staging buffer of the kernels that reduce HBM tables only (24 KB)
 
-// k3: sum_{j,x: c>0} c * ln(c / N_ij).  Virtual lane v (0..255) owns parent configurations v,
-// v+256, ...; a block of fewer than 256 threads runs several virtual lanes per thread (a warp
-// always holds 32 consecutive virtual lanes), so the bits do not depend on the block size.
-template <bool FROM_GLOBAL>
-__device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh) {
-    for (u32 vl = threadIdx.x; vl < RED_LANES; vl += blockDim.x) {
-        double acc = 0.0;
-        for (u32 j = vl; j < q; j += RED_LANES) {
-            const u32 *row = tab + (size_t)j * r;
-            u32 nij = 0;
-            for (int x = 0; x < r; ++x) nij += FROM_GLOBAL ? __ldcg(row + x) : row[x];
-            if (nij) {
-                double dn = (double)nij;
-                for (int x = 0; x < r; ++x) {
-                    u32 c = FROM_GLOBAL ? __ldcg(row + x) : row[x];
-                    if (c) acc += (double)c * log((double)c / dn);
-                }
+// k3.  Virtual lane v (0..255) owns parent configurations v, v+256, ... and folds their terms
+// into its accumulator in (j, x) order; a block of fewer than 256 threads runs two virtual lanes
+// per thread (a warp always holds 32 consecutive virtual lanes), so the bits do not depend on
+// the block size.  `row` is a functor (row pointer, accumulator) that adds one parent
+// configuration's terms.
+//
+// Tables in shared memory are read in place.  Tables in HBM are staged through `stage` (cap
+// words of shared memory) in pieces of cap / r consecutive configurations, loaded by the whole
+// block with coalesced, independent loads: one CTA walking a 200 k-cell table with dependent
+// 4-byte loads (the first version) spent ~150 us in L2 latency per family.  The order in which a
+// lane meets its configurations is the same either way.
+template <bool FROM_GLOBAL, class RowFn>
+__device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap, RowFn row) {
+    double acc[2] = {0.0, 0.0};
+    if (!FROM_GLOBAL) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const u32 vl = threadIdx.x + u * blockDim.x;
+            if (vl < RED_LANES && (u == 0 || blockDim.x < RED_LANES))
+                for (u32 j = vl; j < q; j += RED_LANES) row(tab + (size_t)j * r, acc[u]);
+        }
+    } else {
+        const u32 J = cap / (u32)r;   // configurations per piece (r <= 255, cap >= 2048)
+        for (u32 base = 0; base < q; base += J) {
+            const u32 cnt = min(J, q - base), ncell = cnt * (u32)r;
+            const u32 *src = tab + (size_t)base * r;
+            __syncthreads();          // the previous piece has been consumed
+            u32 i = threadIdx.x;
+            for (; i + 7 * blockDim.x < ncell; i += 8 * blockDim.x) {
+                u32 v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __ldcg(src + i + e * blockDim.x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) stage[i + e * blockDim.x] = v[e];
+            }
+            for (; i < ncell; i += blockDim.x) stage[i] = __ldcg(src + i);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const u32 vl = threadIdx.x + u * blockDim.x;
+                if (vl < RED_LANES && (u == 0 || blockDim.x < RED_LANES))
+                    for (u32 j = base + ((vl - base) & (RED_LANES - 1)); j < base + cnt; j += RED_LANES)
+                        row(stage + (size_t)(j - base) * r, acc[u]);
             }
         }
+    }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if ((vl & 31) == 0) sh[vl >> 5] = acc;
+    for (int u = 0; u < 2; ++u) {
+        const u32 vl = threadIdx.x + u * blockDim.x;
+        if (vl < RED_LANES && (u == 0 || blockDim.x < RED_LANES)) {
+            double t = acc[u];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            if ((vl & 31) == 0) sh[vl >> 5] = t;
+        }
     }
     __syncthreads();
     double t = 0.0;
     if (threadIdx.x == 0)
         for (int w = 0; w < RED_LANES / 32; ++w) t += sh[w];
     return t;
+}
+
+// sum_{j,x: c>0} c * ln(c / N_ij)
+template <bool FROM_GLOBAL>
+__device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap) {
+    return reduce_rows<FROM_GLOBAL>(tab, q, r, sh, stage, cap, [r](const u32 *row, double &acc) {
+        u32 nij = 0;
+        for (int x = 0; x < r; ++x) nij += row[x];
+        if (nij) {
+            const double dn = (double)nij;
+            for (int x = 0; x < r; ++x) {
+                const u32 c = row[x];
+                if (c) acc += (double)c * log((double)c / dn);
+            }
+        }
+    });
 }
 
 // Bayesian-Dirichlet family term (bnlearn "bde" = BDeu, "k2") on the same counts, same lane order:
 // sum_j [ lgamma(a_ij) - lgamma(a_ij + N_ij) + sum_x ( lgamma(a_ijk + c) - lgamma(a_ijk) ) ].
 template <bool FROM_GLOBAL>
-__device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double a_ij, double a_ijk, double *sh) {
+__device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double a_ij, double a_ijk, double *sh,
+                                            u32 *stage, u32 cap) {
     const double lg_ij = lgamma(a_ij), lg_ijk = lgamma(a_ijk);
-    for (u32 vl = threadIdx.x; vl < RED_LANES; vl += blockDim.x) {
-        double acc = 0.0;
-        for (u32 j = vl; j < q; j += RED_LANES) {
-            const u32 *row = tab + (size_t)j * r;
-            u32 nij = 0;
-            double s = 0.0;
-            for (int x = 0; x < r; ++x) {
-                u32 c = FROM_GLOBAL ? __ldcg(row + x) : row[x];
-                nij += c;
-                if (c) s += lgamma(a_ijk + (double)c) - lg_ijk;
-            }
-            if (nij) acc += (lg_ij - lgamma(a_ij + (double)nij)) + s;
+    return reduce_rows<FROM_GLOBAL>(tab, q, r, sh, stage, cap, [=](const u32 *row, double &acc) {
+        u32 nij = 0;
+        double s = 0.0;
+        for (int x = 0; x < r; ++x) {
+            const u32 c = row[x];
+            nij += c;
+            if (c) s += lgamma(a_ijk + (double)c) - lg_ijk;
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if ((vl & 31) == 0) sh[vl >> 5] = acc;
-    }
-    __syncthreads();
-    double t = 0.0;
-    if (threadIdx.x == 0)
-        for (int w = 0; w < RED_LANES / 32; ++w) t += sh[w];
-    return t;
+        if (nij) acc += (lg_ij - lgamma(a_ij + (double)nij)) + s;
+    });
 }
 
 // The cached family term: log-likelihood (penalty applied at gather time) or a BD score.
+// FROM_GLOBAL: `stage` / `cap` = shared-memory staging buffer (see reduce_rows).
 template <bool FROM_GLOBAL>
-__device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab, const FamMeta &m, double *sh) {
-    if (a.bd_mode == 0) return family_loglik<FROM_GLOBAL>(tab, m.q, m.r, sh);
+__device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab, const FamMeta &m, double *sh,
+                                              u32 *stage = nullptr, u32 cap = 0) {
+    if (a.bd_mode == 0) return family_loglik<FROM_GLOBAL>(tab, m.q, m.r, sh, stage, cap);
     double a_ijk = a.bd_mode == 1 ? a.iss / ((double)m.q * (double)m.r) : 1.0;
-    return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh);
+    return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh, stage, cap);
 }
 
 // RANGE (class 3 when the rows dwarf the table): the table does not fit one CTA's shared memory,
@@ -546,7 +588,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        ll = family_term<true>(a, tab, m, s_red);
+        ll = family_term<true>(a, tab, m, s_red, s_hist, a.stage_words);
     }
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
@@ -559,12 +601,13 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njobs) {
     __shared__ FamMeta m;
     __shared__ double s_red[32];
+    __shared__ u32 s_stage[STAGE_WORDS];
     const int j = blockIdx.x;
     if (j >= njobs) return;
     if (a.donor && a.donor[j] >= 0) return;   // derived families are reduced by k_derive
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
-    double ll = family_term<true>(a, a.arena + a.table_off[j], m, s_red);
+    double ll = family_term<true>(a, a.arena + a.table_off[j], m, s_red, s_stage, STAGE_WORDS);
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
         a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
@@ -574,24 +617,30 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
 // Derived families.  The donor's table is the joint table over a superset of {y} + Q in the
 // donor's own axis order (its parents ascending, its child last).  Target cell t = (digits over
 // Q ascending, then y) maps to the donor offset sum_v digit_v * stride_donor(v); the donor's
-// extra axes are summed out.  One CTA per derived family; levels (number of parents) run high to
-// low so a donor that is itself derived is complete.  Then the usual fp64 reduce.
+// extra axes are summed out.  One launch per level (number of parents), high to low, so a donor
+// that is itself derived is complete (level_list = the families of this level).  A family is shared out over up to DERIVE_CHUNKS CTAs (one per
+// ~4096 donor cells read: a 9261-cell table summed out of a 194 k-cell donor by a single CTA
+// took 300 us of dependent L2 loads); the last chunk to finish (atomic ticket) runs the usual
+// fp64 reduce.
+constexpr int DERIVE_CHUNKS = 16;
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__restrict__ derived_list, int level) {
+__global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__restrict__ level_list, int dch,
+                                                    const u32 *__restrict__ cells_arr) {
     __shared__ FamMeta m, md;
     __shared__ double s_red[32];
+    __shared__ u32 s_stage[STAGE_WORDS];
     __shared__ u32 s_stride[KMAX + 1];   // donor stride of own axis q (parents 0..k-1, child k)
     __shared__ u32 s_xstride[KMAX + 1], s_xrad[KMAX + 1];   // the donor's extra axes
     __shared__ u32 s_nx, s_xcells;
-    __shared__ int s_go;
-    const int j = derived_list[blockIdx.x];
+    __shared__ int s_last;
+    const int j = level_list[blockIdx.x / dch];
+    const u32 chunk = blockIdx.x % dch;
+    const u32 nchunks = min((u32)dch, max(1u, cells_arr[a.donor[j]] / 4096u));
+    if (chunk >= nchunks) return;
     if (threadIdx.x == 0) {
         const long long Wk = a.W64 + 1;
         const u64 *key = a.keys + (a.key_base + j) * Wk;
-        int pc = 0;
-        for (int w = 0; w < a.W64; ++w) pc += __popcll(key[1 + w]);
-        s_go = (pc == level);
-        if (s_go) {
+        {
             decode_family(key, a.W64, a.card, m);
             decode_family(a.keys + (a.key_base + a.donor[j]) * Wk, a.W64, a.card, md);
             for (int q = 0; q <= m.k; ++q) s_stride[q] = 0;
@@ -617,12 +666,12 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
         }
     }
     __syncthreads();
-    if (!s_go) return;
     const u32 *dt = a.arena + a.table_off[a.donor[j]];
     u32 *mt = a.arena + a.table_off[j];
     const u32 nx = s_nx, xcells = s_xcells, cells = m.cells;
+    const u32 t0 = (u32)((u64)cells * chunk / nchunks), t1 = (u32)((u64)cells * (chunk + 1) / nchunks);
     const int k = m.k;
-    for (u32 t = threadIdx.x; t < cells; t += THREADS) {
+    for (u32 t = t0 + threadIdx.x; t < t1; t += THREADS) {
         u32 rem = t / (u32)m.r;
         size_t src = (size_t)(t - rem * (u32)m.r) * s_stride[k];
         for (int q = k - 1; q >= 0; --q) {
@@ -631,21 +680,37 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
             rem = nxt;
         }
         u32 s = 0;
-        for (u32 e = 0; e < xcells; ++e) {
-            u32 er = e;
-            size_t o = src;
-            for (u32 ax = 0; ax < nx; ++ax) {
-                u32 en = er / s_xrad[ax];
-                o += (size_t)(er - en * s_xrad[ax]) * s_xstride[ax];
-                er = en;
+        if (nx == 1) {   // one extra axis (the common case): independent strided loads
+            const u32 *p = dt + src;
+            const size_t xs = s_xstride[0];
+            u32 e = 0;
+            for (; e + 4 <= xcells; e += 4) {
+                u32 v0 = __ldcg(p + (e + 0) * xs), v1 = __ldcg(p + (e + 1) * xs), v2 = __ldcg(p + (e + 2) * xs),
+                    v3 = __ldcg(p + (e + 3) * xs);
+                s += v0 + v1 + v2 + v3;
             }
-            s += __ldcg(dt + o);
+            for (; e < xcells; ++e) s += __ldcg(p + e * xs);
+        } else {
+            for (u32 e = 0; e < xcells; ++e) {
+                u32 er = e;
+                size_t o = src;
+                for (u32 ax = 0; ax < nx; ++ax) {
+                    u32 en = er / s_xrad[ax];
+                    o += (size_t)(er - en * s_xrad[ax]) * s_xstride[ax];
+                    er = en;
+                }
+                s += __ldcg(dt + o);
+            }
         }
         mt[t] = s;
     }
     __threadfence();
     __syncthreads();
-    double ll = family_term<true>(a, mt, m, s_red);
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.done + j, 1u) == nchunks - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double ll = family_term<true>(a, mt, m, s_red, s_stage, STAGE_WORDS);
     if (threadIdx.x == 0) {
         a.ll_out[a.key_base + j] = ll;
         a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
