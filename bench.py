@@ -451,8 +451,8 @@ def main():
     # roofline of the dominant kernel = the count-kernel class that took most of the step
     kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory; 32 lane replicas <= 192 cells, 16 <= 384)",
                "k_count<512,false> (tables <= 12288 cells in shared memory)",
-               "k_count<512,false> (tables <= 49152 cells in shared memory)",
-               "k_count<512,false,true> / k_count<256,true> (tables > 49152 cells: shared-memory sub-range passes, or L2 atomics when rows are few)"]
+               "k_count<1024,false> (tables <= 49152 cells in shared memory, one CTA per SM)",
+               "k_count<1024,false,true> / k_count<256,true> (tables > 49152 cells: shared-memory sub-range passes, or L2 atomics when rows are few)"]
     dom = int(np.argmax(prof["class_ms"]))
     dom_ms, dom_launches = prof["class_ms"][dom], max(prof["class_launches"][dom], 1)
     achieved = prof["class_alg_bytes"][dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

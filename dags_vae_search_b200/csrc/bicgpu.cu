@@ -126,6 +126,7 @@ struct bic_ctx {
         long long pack2_min_rows = 1ll << 20;  // BIC_PACK2_MIN_ROWS
         long long derive_min_rows = 1ll << 20;
         long long l2_window = 32ll << 20;      // BIC_L2_WINDOW_MB: dataset bytes of one row slice kept L2-resident
+        long long l2_window_max = 256ll << 20; // BIC_L2_WINDOW_MAX_MB: window when all families of a class are resident at once
         u32 class0_words = CLASS0_WORDS;       // BIC_CLASS0_WORDS: shared-memory words of a class-0 CTA
         int class0_threads = 256;              // BIC_CLASS0_THREADS: 256, 512 or 1024
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
@@ -137,6 +138,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_NO_PACK2")) pack2 = atoi(e) == 0;
             if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
             if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
+            if (const char *e = getenv("BIC_L2_WINDOW_MAX_MB")) { long long mb = atoll(e); if (mb > 0) l2_window_max = mb << 20; }
             if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
@@ -330,10 +332,8 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     NeedArgs na;
     na.all = all_tables ? 1 : 0;
     const long long smax = std::max<long long>(1, c->N / 65536);
-    const long long L2_WINDOW = c->tune.l2_window;
-    const long long s_l2 = ((long long)c->n * c->N + L2_WINDOW - 1) / L2_WINDOW;
     // measured on B200 (profiles/): streaming loads, L2 atomics, rows per second one CTA of a class counts
-    const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9;
+    const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9, CTA_SETUP_S = 4.0e-6;
     const long long resident[NCLASS] = {4, 2, 1, 4};          // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
     // class 3 in passes over shared-memory sub-ranges (k_count<512, false, true>) when every table
     // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
@@ -357,11 +357,19 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
             double best = 0.0;
             for (long long s = 1; s <= hi; ++s) {
                 const double waves = (double)((ctas * s + slots - 1) / slots);
-                const double t = waves * ((double)c->N / (double)s) / CTA_ROWS_PER_S + (s > 1 || all_tables ? (double)s * merge1 : 0.0);
+                const double t = waves * (((double)c->N / (double)s) / CTA_ROWS_PER_S + CTA_SETUP_S) + (s > 1 || all_tables ? (double)s * merge1 : 0.0);
                 if (s == 1 || t < best * 0.97) { best = t; S = s; }
             }
             if (!c->tune.slice_model) S = std::min(smax, ((long long)c->sm_count * 8 + cnt - 1) / cnt);
-            // (b): L2 windows
+            // (b): L2 windows.  Families that run one after another (many more than the GPU holds
+            // at once) need a window that stays in L2 until the last of them has passed: 32 MB.
+            // Families that are all resident at once sweep the rows side by side anyway; wider
+            // windows then mean fewer CTAs to set up, zero, compact and merge (pigs-shaped local
+            // moves: 1.65 ms with 32 MB windows, 1.04-1.09 ms with 160-320 MB; diabetes-shaped
+            // best at 96-160 MB).  In between, the window shrinks with the number of rounds.
+            const long long win = !c->tune.slice_model ? c->tune.l2_window :
+                std::max(c->tune.l2_window, std::min(c->tune.l2_window_max, c->tune.l2_window_max * slots / ctas));
+            const long long s_l2 = ((long long)c->n * c->N + win - 1) / win;
             if (s_l2 > S && !rng3) {
                 const double row_bytes = (double)h.alg_bytes[k] - 4.0 * (double)h.class_cells[k];
                 const double saved = (row_bytes - (double)c->n * (double)c->N) / HBM_BPS;
@@ -663,7 +671,7 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
             k_count_bad<<<nblk(Bc, 256), 256, 0, c->stream>>>(c->dag_bad.as<uint8_t>(), Bc, c->d_hdr); LAUNCH(c);
         } else {
             if (n > 128) k_acyclic<true><<<(unsigned)Bc, ACYC_WIDE_THREADS, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
-                                                                             c->dag_bad.as<uint8_t>(), c->d_hdr); 
+                                                                             c->dag_bad.as<uint8_t>(), c->d_hdr);
             else k_acyclic<false><<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
                                                                              c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
         }
