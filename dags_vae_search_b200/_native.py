@@ -32,7 +32,7 @@ SYMBOLS = [
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
     "bic_cache_stats", "bic_cache_export", "bic_cache_import", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
-    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy", "bic_comm_mode",
+    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy", "bic_comm_mode", "bic_plan_slices",
 ]
 
 
@@ -48,6 +48,37 @@ class BicError(Exception):
 class CacheStats(ctypes.Structure):
     _fields_ = [("families", ctypes.c_int64), ("capacity", ctypes.c_int64), ("lookups", ctypes.c_int64),
                 ("misses", ctypes.c_int64), ("bytes", ctypes.c_int64)]
+
+
+class PlanIn(ctypes.Structure):
+    _fields_ = [("sm_count", ctypes.c_int32), ("N", ctypes.c_int64), ("n", ctypes.c_int32), ("max_cells", ctypes.c_int64),
+                ("tables_in_hbm", ctypes.c_int32), ("class_count", ctypes.c_int64 * 4), ("class_cells", ctypes.c_int64 * 4),
+                ("class_alg_bytes", ctypes.c_int64 * 4)]
+
+
+class PlanOut(ctypes.Structure):
+    _fields_ = [("slices", ctypes.c_int32 * 4), ("ranged", ctypes.c_int32), ("passes", ctypes.c_int32)]
+
+
+def plan_slices(N: int, n: int, families, sm_count: int = 148, tables_in_hbm: bool = False) -> dict:
+    """The launch plan the library would use for one batch of new families (host arithmetic only,
+    works without a GPU).  ``families`` = iterable of (k, cells): number of parents and q*r."""
+    bounds = (2048, 12288, 49152)
+    pin = PlanIn(sm_count=sm_count, N=N, n=n, max_cells=0, tables_in_hbm=int(tables_in_hbm))
+    for k, cells in families:
+        cls = sum(cells > b for b in bounds)
+        pin.class_count[cls] += 1
+        pin.class_cells[cls] += cells
+        pin.class_alg_bytes[cls] += (k + 1) * N + 4 * cells
+        pin.max_cells = max(pin.max_cells, cells)
+    out = PlanOut()
+    L = lib()
+    L.bic_plan_slices.argtypes = [ctypes.POINTER(PlanIn), ctypes.POINTER(PlanOut)]
+    L.bic_plan_slices.restype = ctypes.c_int
+    rc = L.bic_plan_slices(ctypes.byref(pin), ctypes.byref(out))
+    if rc != 0:
+        raise BicError(rc, "bic_plan_slices: bad argument")
+    return {"slices": list(out.slices), "ranged": bool(out.ranged), "passes": int(out.passes)}
 
 
 class Profile(ctypes.Structure):

@@ -308,6 +308,72 @@ int refresh_ntotal(bic_ctx *c) {
     return BIC_OK;
 }
 
+// Plan of one run_count(): row slices per family for each count-kernel class, and whether class 3
+// is counted in shared-memory sub-range passes.  Pure host arithmetic (exported as bic_plan_slices
+// so that the CPU test suite can exercise it).
+//
+// Slicing the rows has two purposes and a price.  (a) Few families -> enough CTAs to fill the GPU.
+// (b) A dataset larger than L2 -> items run slice-major, so all resident CTAs sweep the same
+// window of rows and each column segment comes from HBM once per launch instead of once per
+// family.  The price: every slice sets up, zeroes, compacts and merges its shared-memory table
+// into HBM with one L2 atomic per non-zero cell.  Versions a-h always cut into 32 MB windows; for
+// 64 diabetes-shaped local-move candidates (5 GB of rows, a few dozen large-table families) that
+// meant 162 slices whose merges cost 3x the counting itself.  Never under 64K rows per slice.
+void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_out_t &out) {
+    const long long smax = std::max<long long>(1, in.N / 65536);
+    // measured on B200 (profiles/): streaming loads, L2 atomics, rows per second one CTA counts, CTA set-up
+    const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9, CTA_SETUP_S = 4.0e-6;
+    const long long resident[NCLASS] = {4, 2, 1, 4};   // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
+    // class 3 in passes over shared-memory sub-ranges (k_count<1024, false, true>) when every table
+    // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
+    const long long span = CLASS2_CELLS;
+    const int P3 = (int)((in.max_cells + span - 1) / span);
+    const bool ranged = in.class_count[3] > 0 && tune.range_passes > 0 && P3 <= tune.range_passes &&
+                        in.N >= 4ll * in.max_cells;
+    out.ranged = ranged ? 1 : 0;
+    out.passes = ranged ? P3 : 1;
+    for (int k = 0; k < NCLASS; ++k) {
+        const long long cnt = in.class_count[k];
+        long long S = 1;
+        if (cnt > 0) {
+            // (a): the slice count that minimises rounds x (rows per CTA + set-up) + merge traffic.
+            // Whole rounds matter when a class keeps one CTA per SM: 297 CTAs on 148 SMs take
+            // three rounds, not two.
+            const bool rng3 = k == 3 && ranged;
+            const long long ctas = cnt * (rng3 ? P3 : 1);
+            const long long slots = (long long)in.sm_count * (rng3 ? 1 : resident[k]);
+            const long long hi = std::min(rng3 ? std::min(smax, in.N / (4ll * in.max_cells)) : smax,
+                                          std::max<long long>(1, 4 * slots / ctas));
+            const double merge1 = (k == 3 && !ranged) ? 0.0 : (double)in.class_cells[k] / RED_PER_S;
+            double best = 0.0;
+            for (long long s = 1; s <= hi; ++s) {
+                const double rounds = (double)((ctas * s + slots - 1) / slots);
+                const double t = rounds * (((double)in.N / (double)s) / CTA_ROWS_PER_S + CTA_SETUP_S) +
+                                 ((s > 1 || in.tables_in_hbm) ? (double)s * merge1 : 0.0);
+                if (s == 1 || t < best * 0.97) { best = t; S = s; }
+            }
+            if (!tune.slice_model) S = std::min(smax, ((long long)in.sm_count * 8 + cnt - 1) / cnt);
+            // (b): L2 windows.  Families that run one after another (many more than the GPU holds
+            // at once) need a window that stays in L2 until the last of them has passed: 32 MB.
+            // Families that are all resident at once sweep the rows side by side anyway; wider
+            // windows then mean fewer CTAs to set up, zero, compact and merge (pigs-shaped local
+            // moves: 1.65 ms with 32 MB windows, 1.04-1.09 ms with 160-320 MB; diabetes-shaped
+            // best at 96-160 MB).  In between, the window shrinks with the number of rounds.
+            // Taken only when the HBM traffic it saves (the class's algorithmic row bytes beyond
+            // one pass over the dataset) outweighs the extra merges.
+            const long long win = !tune.slice_model ? tune.l2_window :
+                std::max(tune.l2_window, std::min(tune.l2_window_max, tune.l2_window_max * slots / ctas));
+            const long long s_l2 = ((long long)in.n * in.N + win - 1) / win;
+            if (s_l2 > S && !rng3) {
+                const double row_bytes = (double)in.class_alg_bytes[k] - 4.0 * (double)in.class_cells[k];
+                const double saved = (row_bytes - (double)in.n * (double)in.N) / HBM_BPS;
+                if (!tune.slice_model || saved > (double)(s_l2 - S) * merge1) S = s_l2;
+            }
+        }
+        out.slices[k] = (int)std::max<long long>(1, std::min(smax, S));
+    }
+}
+
 // Count (and reduce) `njobs` families described in c->cells_arr / c->class_jobs; the header in
 // pinned memory holds the class counts.  keys/key_base select registry or key buffer.
 int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, long long max_jobs,
@@ -320,64 +386,25 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     for (int l = 0; l < DERIVE_LEVELS; ++l) lvl_count[l] = with_donors ? h.lvl_count[l] : 0;   // header is re-fetched below
     const bool all_tables = want_tables || sharded || n_derived > 0;
 
-    // Row slices per family.  Two reasons to slice: (a) few families -> enough CTAs to fill the
-    // GPU (two waves of the CTAs a class keeps resident per SM); (b) a dataset larger than L2 ->
-    // items run slice-major, so all resident CTAs sweep the same window of rows (all n columns of
-    // one slice <= L2_WINDOW bytes) and each column segment comes from HBM once per launch
-    // instead of once per family.  (b) has a price: every slice merges its shared-memory table
-    // into HBM with one L2 atomic per non-zero cell, so it is taken only when the HBM traffic it
-    // saves (the class's algorithmic row bytes beyond one pass over the dataset) outweighs those
-    // merges — with 5 GB of rows and a few dozen large-table families (diabetes-shaped local
-    // moves) 160 windows cost 3x the counting itself.  Never under 64K rows per slice.
+    // Row slices per family and how class 3 is counted: plan_count() below.
     NeedArgs na;
     na.all = all_tables ? 1 : 0;
-    const long long smax = std::max<long long>(1, c->N / 65536);
-    // measured on B200 (profiles/): streaming loads, L2 atomics, rows per second one CTA of a class counts
-    const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9, CTA_SETUP_S = 4.0e-6;
-    const long long resident[NCLASS] = {4, 2, 1, 4};          // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
-    // class 3 in passes over shared-memory sub-ranges (k_count<512, false, true>) when every table
-    // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
+    bic_plan_in_t pin;
+    pin.sm_count = c->sm_count; pin.N = c->N; pin.n = c->n; pin.max_cells = h.max_cells; pin.tables_in_hbm = all_tables ? 1 : 0;
+    for (int k = 0; k < NCLASS; ++k) {
+        pin.class_count[k] = h.class_count[k];
+        pin.class_cells[k] = (long long)h.class_cells[k];
+        pin.class_alg_bytes[k] = (long long)h.alg_bytes[k];
+    }
+    bic_plan_out_t plan;
+    plan_count(pin, c->tune, plan);
     const u32 span = CLASS2_CELLS;
-    const int P3 = (int)((h.max_cells + span - 1) / span);
-    const bool ranged = h.class_count[3] && c->tune.range_passes > 0 && P3 <= c->tune.range_passes &&
-                        c->N >= 4ll * (long long)h.max_cells;
+    const int P3 = plan.passes;
+    const bool ranged = plan.ranged != 0;
     bool any_table = all_tables;
     for (int k = 0; k < NCLASS; ++k) {
-        const long long cnt = h.class_count[k];
-        long long S = 1;
-        if (cnt) {
-            // (a): slices that minimise waves x rows per item + merge traffic (whole waves matter
-            // when a class keeps one CTA per SM: 297 items on 148 SMs take three rounds, not two)
-            const bool rng3 = k == 3 && ranged;
-            const long long ctas = cnt * (rng3 ? P3 : 1);
-            const long long slots = (long long)c->sm_count * (rng3 ? 1 : resident[k]);
-            const long long hi = std::min(rng3 ? std::min(smax, c->N / (4ll * (long long)h.max_cells)) : smax,
-                                          std::max<long long>(1, 4 * slots / ctas));
-            const double merge1 = (k == 3 && !ranged) ? 0.0 : (double)h.class_cells[k] / RED_PER_S;
-            double best = 0.0;
-            for (long long s = 1; s <= hi; ++s) {
-                const double waves = (double)((ctas * s + slots - 1) / slots);
-                const double t = waves * (((double)c->N / (double)s) / CTA_ROWS_PER_S + CTA_SETUP_S) + (s > 1 || all_tables ? (double)s * merge1 : 0.0);
-                if (s == 1 || t < best * 0.97) { best = t; S = s; }
-            }
-            if (!c->tune.slice_model) S = std::min(smax, ((long long)c->sm_count * 8 + cnt - 1) / cnt);
-            // (b): L2 windows.  Families that run one after another (many more than the GPU holds
-            // at once) need a window that stays in L2 until the last of them has passed: 32 MB.
-            // Families that are all resident at once sweep the rows side by side anyway; wider
-            // windows then mean fewer CTAs to set up, zero, compact and merge (pigs-shaped local
-            // moves: 1.65 ms with 32 MB windows, 1.04-1.09 ms with 160-320 MB; diabetes-shaped
-            // best at 96-160 MB).  In between, the window shrinks with the number of rounds.
-            const long long win = !c->tune.slice_model ? c->tune.l2_window :
-                std::max(c->tune.l2_window, std::min(c->tune.l2_window_max, c->tune.l2_window_max * slots / ctas));
-            const long long s_l2 = ((long long)c->n * c->N + win - 1) / win;
-            if (s_l2 > S && !rng3) {
-                const double row_bytes = (double)h.alg_bytes[k] - 4.0 * (double)h.class_cells[k];
-                const double saved = (row_bytes - (double)c->n * (double)c->N) / HBM_BPS;
-                if (!c->tune.slice_model || saved > (double)(s_l2 - S) * merge1) S = s_l2;
-            }
-        }
-        na.S[k] = (int)std::max<long long>(1, std::min(smax, S));
-        if (cnt && (na.S[k] > 1 || k == 3)) any_table = true;
+        na.S[k] = plan.slices[k];
+        if (h.class_count[k] && (na.S[k] > 1 || k == 3)) any_table = true;
     }
 
     if (any_table) {
@@ -702,6 +729,16 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
 
 // ================================================================================ C ABI
 extern "C" {
+
+int bic_plan_slices(const bic_plan_in_t *in, bic_plan_out_t *out) {
+    if (!in || !out || in->sm_count <= 0 || in->N <= 0 || in->n <= 0 || in->max_cells < 0) return BIC_ERR_ARG;
+    for (int k = 0; k < NCLASS; ++k)
+        if (in->class_count[k] < 0 || in->class_cells[k] < 0 || in->class_alg_bytes[k] < 0) return BIC_ERR_ARG;
+    bic_ctx::Tuning tune;
+    tune.from_env();
+    plan_count(*in, tune, *out);
+    return BIC_OK;
+}
 
 int bic_version(void) { return BICGPU_VERSION; }
 

@@ -164,6 +164,30 @@ int bic_profile_enable(bic_ctx *ctx, int on);
 int bic_profile_reset(bic_ctx *ctx);
 int bic_profile_get(bic_ctx *ctx, bic_profile_t *out);
 
+/* ---- launch planning (host arithmetic only; no GPU needed) --------------------------------
+ * How one batch of new families is cut into count-kernel work: row slices per family for each
+ * table-size class and whether class 3 (tables above one CTA's shared memory) is counted in
+ * shared-memory sub-range passes or straight into HBM.  The library calls the same function
+ * internally; it is exported so that the planning rules can be tested without a GPU.  The result
+ * never changes a count or a score, only the time it takes. */
+typedef struct {
+    int32_t sm_count;          /* SMs of the device (B200: 148)                                 */
+    int64_t N;                 /* rows on this GPU                                              */
+    int32_t n;                 /* variables                                                     */
+    int64_t max_cells;         /* largest q*r among the families                                */
+    int32_t tables_in_hbm;     /* 1: every table is merged into HBM anyway (row-sharded, derived
+                                * families present, bic_count_families)                         */
+    int64_t class_count[4];    /* families per class (<= 2048 / 12288 / 49152 cells / larger)   */
+    int64_t class_cells[4];    /* sum of q*r per class                                          */
+    int64_t class_alg_bytes[4];/* sum of (k+1)*N + 4*q*r per class                              */
+} bic_plan_in_t;
+typedef struct {
+    int32_t slices[4];         /* row slices per family, per class                              */
+    int32_t ranged;            /* 1: class 3 in shared-memory sub-range passes                  */
+    int32_t passes;            /* sub-range passes per (family, slice) when ranged, else 1      */
+} bic_plan_out_t;
+int bic_plan_slices(const bic_plan_in_t *in, bic_plan_out_t *out);
+
 /* ---- row sharding over several GPUs (one process per GPU) ------------------------------
  * Each rank holds N_rank rows of the same n columns.  After bic_comm_init every scoring call
  * must be made collectively with identical family / DAG arguments on every rank: partial

@@ -213,3 +213,58 @@ def test_bench_workload_definitions():
     # the re-sampled asia rows keep the marginals of the bundled data within sampling noise
     base = pkg.load_dataset("asia")[0]
     assert np.abs(codes.mean(axis=1) - base.mean(axis=1)).max() < 0.02
+
+
+# ---------------------------------------------------------------- launch planning (no GPU)
+def test_launch_plan_rules(monkeypatch):
+    """bic_plan_slices is the host arithmetic the library uses to cut a batch of new families into
+    count-kernel work items (csrc/bicgpu.cu:plan_count).  It never changes a result, only the time,
+    so what is pinned here are its rules, on the shapes of the BASELINE configs."""
+    for v in ("BIC_SLICE_MODEL", "BIC_RANGE_PASSES", "BIC_L2_WINDOW_MB", "BIC_L2_WINDOW_MAX_MB"):
+        monkeypatch.delenv(v, raising=False)
+    MB = 1 << 20
+
+    def windows(n, N, mb):
+        return -(-n * N // (mb * MB))
+
+    # alarm-shaped step: 17.5 k small-table families run one after another on 370 MB of rows ->
+    # 32 MB L2 windows; no class-3 table
+    N = 10_000_000
+    alarm = nat.plan_slices(N, 37, [(5, 700)] * 17500 + [(6, 4000)] * 1800 + [(6, 16384)])
+    assert alarm["slices"][0] == windows(37, N, 32) and not alarm["ranged"] and alarm["passes"] == 1
+    assert all(1 <= s <= N // 65536 for s in alarm["slices"])
+    # a handful of families of a search step: enough slices to occupy the GPU, well below the window count of a full pass
+    few = nat.plan_slices(N, 37, [(5, 700)] * 40)
+    assert 148 * 4 // 40 <= few["slices"][0] <= 4 * 148 * 4 // 40
+
+    # diabetes-shaped local moves (5.2 GB of rows): the few large-table families are not cut into
+    # 162 L2 windows (their merges would cost more than the counting), class 3 runs in 4 passes
+    N = 12_500_000
+    fams = [(2, 600)] * 240 + [(2, 6000)] * 99 + [(3, 30000)] * 33 + [(3, 194481)] * 7
+    diab = nat.plan_slices(N, 413, fams, tables_in_hbm=True)
+    assert diab["ranged"] and diab["passes"] == 4
+    assert diab["slices"][1] < 20 and diab["slices"][2] < 10 and diab["slices"][3] <= N // (4 * 194481)
+    assert windows(413, N, 256) <= diab["slices"][0] < windows(413, N, 32)      # all resident at once: wide windows
+    pigs = nat.plan_slices(N, 441, [(2, 81)] * 391, tables_in_hbm=True)
+    assert windows(441, N, 256) <= pigs["slices"][0] <= windows(441, N, 128)
+    # the same families with the model off: the 32 MB rule of kernel versions a-h
+    monkeypatch.setenv("BIC_SLICE_MODEL", "0")
+    old = nat.plan_slices(N, 413, fams, tables_in_hbm=True)
+    assert old["slices"][:3] == [windows(413, N, 32)] * 3
+    monkeypatch.delenv("BIC_SLICE_MODEL")
+
+    # few rows: never sliced, and a table much larger than the row count goes straight to HBM
+    sachs = nat.plan_slices(5000, 11, [(4, 243)] * 7000 + [(7, 6561)] * 2000 + [(10, 177147)])
+    assert sachs["slices"] == [1, 1, 1, 1] and not sachs["ranged"]
+    # sub-range passes only up to BIC_RANGE_PASSES sub-ranges and with >= 4 rows per cell
+    assert nat.plan_slices(N, 20, [(8, 49152 * 8)])["passes"] == 8
+    assert not nat.plan_slices(N, 20, [(8, 49152 * 8 + 1)])["ranged"]
+    assert not nat.plan_slices(4 * 194481 - 1, 20, [(3, 194481)])["ranged"]
+    monkeypatch.setenv("BIC_RANGE_PASSES", "0")
+    assert not nat.plan_slices(N, 413, fams)["ranged"]
+    monkeypatch.delenv("BIC_RANGE_PASSES")
+
+    # argument checks
+    bad = nat.PlanIn(sm_count=0, N=10, n=2)
+    out = nat.PlanOut()
+    assert nat.lib().bic_plan_slices(ctypes.byref(bad), ctypes.byref(out)) == -2
