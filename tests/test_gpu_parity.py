@@ -668,6 +668,47 @@ def test_degenerate_shapes():
         assert s.score_adjacency(adj, metric="aic")[0] == -(1 + 2 + 3 * 2 * 3)
 
 
+def test_limits_1024_variables_255_states():
+    """The documented limits: n = 1024 variables (16-word parent masks, block-per-DAG cycle check,
+    warp-per-DAG gather) and 255 states per variable (fp64 reduce staged in pieces of
+    floor(cap / 255) parent configurations; 255 x 255 = 65 025 cells: class 3, counted in two
+    sub-range passes here)."""
+    n, N = 1024, 300_000
+    rng = np.random.default_rng(91)
+    card = rng.choice(np.array([2, 3, 4], dtype=np.int32), size=n)
+    card[[0, 5, 1023]] = 255
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    codes[1023] = (codes[0].astype(np.int32) * 7 + codes[1]) % 255
+    fams = [(1023, [0]), (0, [5]), (5, []), (1022, [0, 1023]), (7, [1, 2, 3, 1021])]
+    # a chain DAG over all 1024 variables plus the edges above; CSR input
+    parents = [[] for _ in range(n)]
+    for i in range(1, n):
+        parents[i].append(i - 1)
+    parents[1023] = [0, 1022]
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(p) for p in parents])
+    flat = np.array([p for ps in parents for p in sorted(ps)], dtype=np.int32)
+    with pkg.BicScorer(codes, card) as s:
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])     # largest table 255 * 255 * r: L2 atomics
+        for (i, ps), t in zip(fams, tabs):
+            assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (i, ps)
+        assert np.array_equal(s.family_counts(1023, [0]), tabs[0])               # alone: two sub-range passes
+        node, foff, fpar = csr_of(fams)
+        want_f = C.score_families(codes, card, node, foff, fpar)
+        assert_scores(s.score_families_csr(node, foff, fpar, no_cache=True), want_f)
+        assert_scores(s.score_families([1023], [[0]], no_cache=True), want_f[:1])
+        got = s.score_csr(off, flat, 1)
+        want = float(np.cumsum(C.score_families(codes, card, np.arange(n, dtype=np.int32), off, flat))[-1])
+        assert got[0] == pytest.approx(want, rel=RTOL)
+        # close the chain into a cycle: 1023 -> 0
+        cyc = [list(p) for p in parents]
+        cyc[0] = [1023]
+        coff = np.zeros(n + 1, dtype=np.int64)
+        coff[1:] = np.cumsum([len(p) for p in cyc])
+        cflat = np.array([p for ps in cyc for p in sorted(ps)], dtype=np.int32)
+        assert np.isnan(s.score_csr(coff, cflat, 1)[0])
+
+
 def test_cache_checkpoint_resume(sachs, tmp_path):
     """Checkpoint / resume of a search: the family cache survives a process restart."""
     codes, card = sachs
