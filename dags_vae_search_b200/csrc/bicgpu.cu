@@ -132,6 +132,7 @@ struct bic_ctx {
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
                                                //   are counted in passes (0: always straight into HBM with L2 atomics)
         int class2_threads = 1024;             // BIC_CLASS2_THREADS: 512 or 1024 (classes 2 and 3-in-passes: one CTA per SM)
+        bool fast_small = true;                // BIC_NO_FAST_SMALL=1: small warm batches take the general pipeline too
         bool slice_model = true;               // BIC_SLICE_MODEL=0: always cut the rows into L2 windows (round-1 versions a-h)
         void from_env() {
             if (const char *e = getenv("BIC_NO_DERIVE")) derive = atoi(e) == 0;
@@ -142,6 +143,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
+            if (const char *e = getenv("BIC_NO_FAST_SMALL")) fast_small = atoi(e) == 0;
             if (const char *e = getenv("BIC_SLICE_MODEL")) slice_model = atoi(e) != 0;
             if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) class0_threads = t; }
         }
@@ -159,6 +161,7 @@ struct bic_ctx {
     int rank_id = 0, world = 1;
     int comm_mode = 0;       // BIC_SHARD_ROWS or BIC_SHARD_FAMILIES
     bool ntotal_dirty = true;
+    bool fast_ok = true;     // small warm batches: try k_score_small first (off after a miss, on again after an all-hit call)
 };
 
 namespace {
@@ -655,6 +658,31 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
     const double pen = metric_penalty(c, metric);
     const bool dev = (flags & BIC_FLAG_DEVICE_PTRS) != 0;
     long long invalid = 0;
+    // Small warm batch (the reference's one-DAG-per-call usage): one launch, one synchronisation.
+    if (fmt == FMT_ADJ && c->fast_ok && c->tune.fast_small && !c->comm && c->reg_count > 0 && c->W64 == 1 && B > 0 &&
+        B * n <= 8192) {
+        TRY(header_reset(c));
+        const uint8_t *adj = nullptr;
+        TRY(stage_in(c, (const uint8_t *)p0, (size_t)B * n * n, flags, c->in_stage, &adj));
+        double *d_out = out;
+        if (!dev) {
+            CU(c->out_stage.ensure((size_t)B * sizeof(double)));
+            d_out = c->out_stage.as<double>();
+        }
+        k_score_small<<<nblk(B, SMALL_WARPS), SMALL_WARPS * 32, 0, c->stream>>>(
+            adj, B, n, c->table, (u32)(c->table_cap - 1), c->regkeys, c->reg_ll, c->reg_np, pen,
+            (flags & BIC_FLAG_NO_CYCLE_CHECK) ? 0 : 1, d_out, c->d_hdr); LAUNCH(c);
+        CU(cudaGetLastError());
+        if (!dev) CU(cudaMemcpyAsync(out, d_out, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TRY(header_fetch(c));
+        if (!(c->h_hdr->err & 8u)) {
+            c->lookups += B * n;
+            if (n_invalid) *n_invalid = c->h_hdr->n_invalid;
+            return finish_call(c);
+        }
+        c->fast_ok = false;   // a family is not cached yet: the general pipeline inserts and counts it
+    }
+    const long long misses0 = c->misses;
     const long long Bs = sub_batch_dags(c);
     std::vector<long long> h_off;   // CSR offsets are needed on the host to slice a host batch
     for (long long b0 = 0; b0 < B; b0 += Bs) {
@@ -722,6 +750,7 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
         TRY(finish_call(c));
     }
     if (n_invalid) *n_invalid = invalid;
+    c->fast_ok = (c->misses == misses0);   // everything was cached: the next small batch may take the short cut
     return BIC_OK;
 }
 

@@ -668,6 +668,58 @@ def test_degenerate_shapes():
         assert s.score_adjacency(adj, metric="aic")[0] == -(1 + 2 + 3 * 2 * 3)
 
 
+def test_small_warm_batches_take_the_one_launch_path(monkeypatch):
+    """Small batches whose families are all cached are scored by one kernel (k_score_small: keys,
+    cycle check, lookup, sum).  Same bits as the general pipeline, same NaN / n_invalid for cyclic
+    DAGs, and a batch with an unseen family falls back (and is then cached)."""
+    for n, N in ((8, 3000), (37, 5000), (64, 2000)):
+        rng = np.random.default_rng(n)
+        card = rng.choice(np.array([2, 3], dtype=np.int32), size=n)
+        codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+        dags = synth.er_candidates(n, 40, n - 1, 2 * n, 3, seed=5)
+        cyc = dags[3].copy()
+        order = synth.topo_order(cyc)
+        cyc[order[-1], order[0]] = 1
+        ps = np.flatnonzero(dags[3][:, order[-1]])
+        if len(ps):
+            cyc[order[0], ps[0]] = 1
+        loop = dags[4].copy()
+        loop[2, 2] = 1
+        batch = np.concatenate([dags, cyc[None], loop[None]])
+        monkeypatch.setenv("BIC_NO_FAST_SMALL", "1")
+        with pkg.BicScorer(codes, card) as s:
+            want, want_bad = s.score_adjacency(batch, return_invalid=True)
+            want_aic = s.score_adjacency(batch, metric="aic")
+            launches_general = s.profile()["kernel_launches"]
+        monkeypatch.delenv("BIC_NO_FAST_SMALL")
+        with pkg.BicScorer(codes, card) as s:
+            cold = s.score_adjacency(batch)                       # cold cache: general pipeline
+            assert np.array_equal(cold, want, equal_nan=True)
+            assert np.array_equal(s.score_adjacency(batch), want, equal_nan=True)   # all cached now, but the last call had misses: general once more
+            before = s.profile()["kernel_launches"]
+            warm, bad = s.score_adjacency(batch, return_invalid=True)
+            assert s.profile()["kernel_launches"] == before + 1   # one launch
+            assert np.array_equal(warm, want, equal_nan=True) and bad == want_bad
+            assert np.isnan(warm[-1]) and np.isnan(warm[-2]) == (not O.is_acyclic(cyc))
+            assert np.array_equal(s.score_adjacency(batch, metric="aic"), want_aic, equal_nan=True)
+            one = np.array([s.score_adjacency(batch[b:b + 1])[0] for b in range(10)])   # the reference's usage: one DAG per call
+            assert np.array_equal(one, want[:10])
+            # an unseen family: falls back, is counted, and the next call is short again
+            fresh = synth.er_candidates(n, 5, n - 1, 2 * n, 3, seed=6)
+            fams0 = s.cache_stats()["families"]
+            got = s.score_adjacency(np.concatenate([batch[:3], fresh]))
+            assert s.cache_stats()["families"] > fams0
+            assert_scores(got[3:], C.score_dags_adj(codes, card, fresh))
+            before = s.profile()["kernel_launches"]
+            s.score_adjacency(fresh)          # all cached, but the last call had misses: general pipeline once more
+            s.score_adjacency(fresh)
+            assert s.profile()["kernel_launches"] > before + 1
+            before = s.profile()["kernel_launches"]
+            again = s.score_adjacency(fresh)
+            assert s.profile()["kernel_launches"] == before + 1 and np.array_equal(again, got[3:])
+        assert launches_general > 10
+
+
 def test_limits_1024_variables_255_states():
     """The documented limits: n = 1024 variables (16-word parent masks, block-per-DAG cycle check,
     warp-per-DAG gather) and 255 states per variable (fp64 reduce staged in pieces of
