@@ -361,11 +361,12 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
             // Families that are all resident at once sweep the rows side by side anyway; wider
             // windows then mean fewer CTAs to set up, zero, compact and merge (pigs-shaped local
             // moves: 1.65 ms with 32 MB windows, 1.04-1.09 ms with 160-320 MB; diabetes-shaped
-            // best at 96-160 MB).  In between, the window shrinks with the number of rounds.
+            // best at 96-160 MB).  In between (only the two ends are measured) the window shrinks with
+            // the number of rounds a slice takes: 128 MB / rounds.
             // Taken only when the HBM traffic it saves (the class's algorithmic row bytes beyond
             // one pass over the dataset) outweighs the extra merges.
             const long long win = !tune.slice_model ? tune.l2_window :
-                std::max(tune.l2_window, std::min(tune.l2_window_max, tune.l2_window_max * slots / ctas));
+                ctas <= slots ? tune.l2_window_max : std::max(tune.l2_window, tune.l2_window_max / 2 * slots / ctas);
             const long long s_l2 = ((long long)in.n * in.N + win - 1) / win;
             if (s_l2 > S && !rng3) {
                 const double row_bytes = (double)in.class_alg_bytes[k] - 4.0 * (double)in.class_cells[k];
