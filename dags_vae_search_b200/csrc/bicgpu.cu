@@ -132,6 +132,7 @@ struct bic_ctx {
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
                                                //   are counted in passes (0: always straight into HBM with L2 atomics)
         int class2_threads = 1024;             // BIC_CLASS2_THREADS: 512 or 1024 (classes 2 and 3-in-passes: one CTA per SM)
+        bool fma_extract = false;              // BIC_FMA_EXTRACT=1: packed path splits its 16-bit lanes on the FMA pipe (experiment)
         bool fast_small = true;                // BIC_NO_FAST_SMALL=1: small warm batches take the general pipeline too
         bool slice_model = true;               // BIC_SLICE_MODEL=0: always cut the rows into L2 windows (round-1 versions a-h)
         void from_env() {
@@ -143,6 +144,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
+            if (const char *e = getenv("BIC_FMA_EXTRACT")) fma_extract = atoi(e) != 0;
             if (const char *e = getenv("BIC_NO_FAST_SMALL")) fast_small = atoi(e) == 0;
             if (const char *e = getenv("BIC_SLICE_MODEL")) slice_model = atoi(e) != 0;
             if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) class0_threads = t; }
@@ -437,6 +439,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.reduce = sharded ? 0 : 1;
     a.donor = (with_donors && n_derived) ? c->donor.as<int>() : nullptr;
     a.bd_mode = c->cache_mode;
+    a.fma_extract = c->tune.fma_extract ? 1 : 0;
     a.iss = c->iss;
     u32 class_count[NCLASS];
     u64 class_alg[NCLASS];

@@ -40,6 +40,7 @@ struct CountArgs {
     double *np_out;          // [key_base + j]  (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
+    int fma_extract;         // packed path: split 16-bit lanes with IMAD.HI / IMAD instead of SHF / LOP3
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
     double iss;
 };
@@ -51,6 +52,7 @@ struct FamMeta {
     u32 R;      // lane replicas of the shared-memory table (power of two, <= 32)
     u32 mul;    // byte offset of a cell = cell * mul  (mul = 4 * R)
     u32 lo4, span4;   // RANGE kernel: byte offset of the CTA's first cell, bytes of its sub-range
+    u32 k16;    // 65536, opaque to the compiler: 16-bit lane extraction as IMAD.HI / IMAD (FMA pipe) instead of SHF / LOP3 (ALU pipe)
     int par[KMAX];
     u32 rad[KMAX];
 };
@@ -252,9 +254,9 @@ __device__ __forceinline__ void unpack2(u32 W, u32 (&u)[4]) {
     u[3] = (W >> 6) & 0x03030303u;
 }
 
-template <int K, bool MASKED>
+template <int K, bool MASKED, bool FMAX>
 __device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 mul, u32 plow_mul,
-                                         u32 *hist, int lim) {
+                                         u32 *hist, int lim, u32 k16) {
     constexpr int C = K + 1;                  // columns, child last
     constexpr int C1 = C > 4 ? C - 4 : 0;     // columns of the high group
 #pragma unroll
@@ -279,7 +281,15 @@ __device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&ra
                 t01 += __byte_perm(hi[s], 0u, 0x4140u) * plow_mul;
                 t23 += __byte_perm(hi[s], 0u, 0x4342u) * plow_mul;
             }
-            const u32 off[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
+            u32 off[4];
+            if (FMAX) {   // the ALU pipe is the co-limiter (76 %): split the lanes on the FMA pipe
+                off[1] = __umulhi(t01, k16);
+                off[0] = t01 - off[1] * k16;
+                off[3] = __umulhi(t23, k16);
+                off[2] = t23 - off[3] * k16;
+            } else {
+                off[0] = t01 & 0xffffu; off[1] = t01 >> 16; off[2] = t23 & 0xffffu; off[3] = t23 >> 16;
+            }
 #pragma unroll
             for (int B = 0; B < 4; ++B)
                 if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, off[B]);
@@ -287,7 +297,7 @@ __device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&ra
     }
 }
 
-template <int K, int THREADS>
+template <int K, int THREADS, bool FMAX>
 __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
                                               long long N, long long g0, long long g1, u32 *hist) {
     constexpr int C = K + 1;
@@ -304,14 +314,14 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
     u32 plow = 1;
 #pragma unroll
     for (int a = C1; a < C; ++a) plow *= rad[a];
-    const u32 mul = m.mul, plow_mul = plow * mul;
+    const u32 mul = m.mul, plow_mul = plow * mul, k16 = m.k16;
     for (long long g = g0 + threadIdx.x; g < g1; g += THREADS) {
         uint4 w[C];
 #pragma unroll
         for (int a = 0; a < C; ++a) w[a] = ld_stream_v4(cp[a] + g * 16);
         const long long row0 = g * 64;
-        if (row0 + 64 <= N) p2_group<K, false>(w, rad, mul, plow_mul, hist, 64);
-        else p2_group<K, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
+        if (row0 + 64 <= N) p2_group<K, false, FMAX>(w, rad, mul, plow_mul, hist, 64, k16);
+        else p2_group<K, true, FMAX>(w, rad, mul, plow_mul, hist, (int)(N - row0), k16);
     }
 }
 
@@ -530,6 +540,7 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         m.R = R;
         m.mul = 4u * R;
         m.lo4 = lo * 4u;
+        m.k16 = 65536u;
         m.span4 = span * 4u;
     }
     __syncthreads();
@@ -546,14 +557,26 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     // R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
-        switch (m.k) {
-            case 0: count_rows_p2<0, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 1: count_rows_p2<1, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 2: count_rows_p2<2, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 3: count_rows_p2<3, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 4: count_rows_p2<4, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 5: count_rows_p2<5, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            default: count_rows_p2<6, THREADS>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+        if (a.fma_extract) {
+            switch (m.k) {
+            case 0: count_rows_p2<0, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 1: count_rows_p2<1, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 2: count_rows_p2<2, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 3: count_rows_p2<3, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 4: count_rows_p2<4, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 5: count_rows_p2<5, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+                default: count_rows_p2<6, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            }
+        } else {
+            switch (m.k) {
+            case 0: count_rows_p2<0, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 1: count_rows_p2<1, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 2: count_rows_p2<2, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 3: count_rows_p2<3, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 4: count_rows_p2<4, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            case 5: count_rows_p2<5, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+                default: count_rows_p2<6, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
+            }
         }
     } else
     switch (m.k) {
