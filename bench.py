@@ -482,6 +482,7 @@ def main():
         "family_count_rows_per_sec": prof["rows_counted"] / (prof["count_ms"] * 1e-3) if prof["count_ms"] > 0 else None,
         "families_counted_per_step": prof["families_counted"] / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0,   # north_star quotes ~8 TB/s
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernels[dom],
                      "launches": dom_launches, "ms_per_launch": dom_ms / dom_launches,
                      "alg_bytes_per_launch": prof["class_alg_bytes"][dom] / dom_launches,
