@@ -18,6 +18,7 @@ FLAG_DEVICE_PTRS = 1
 FLAG_NO_CYCLE_CHECK = 2
 FLAG_NO_CACHE = 4
 FLAG_NO_DERIVE = 8
+FLAG_LOCAL_BATCH = 16
 METRICS = {"bic": 0, "loglik": 1, "aic": 2, "bde": 3, "k2": 4}
 
 STATUS_NAMES = {
@@ -28,7 +29,8 @@ STATUS_NAMES = {
 
 # every symbol include/bicgpu.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_sync", "bic_set_iss",
+    "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_wait_stream", "bic_sync", "bic_set_iss",
+    "bic_dataset_fingerprint", "bic_score_dags_wire16",
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
     "bic_cache_stats", "bic_cache_export", "bic_cache_import", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
@@ -57,7 +59,8 @@ class PlanIn(ctypes.Structure):
 
 
 class PlanOut(ctypes.Structure):
-    _fields_ = [("slices", ctypes.c_int32 * 4), ("ranged", ctypes.c_int32), ("passes", ctypes.c_int32)]
+    _fields_ = [("slices", ctypes.c_int32 * 4), ("ranged", ctypes.c_int32), ("passes", ctypes.c_int32),
+                ("cluster", ctypes.c_int32)]
 
 
 def plan_slices(N: int, n: int, families, sm_count: int = 148, tables_in_hbm: bool = False) -> dict:
@@ -78,7 +81,7 @@ def plan_slices(N: int, n: int, families, sm_count: int = 148, tables_in_hbm: bo
     rc = L.bic_plan_slices(ctypes.byref(pin), ctypes.byref(out))
     if rc != 0:
         raise BicError(rc, "bic_plan_slices: bad argument")
-    return {"slices": list(out.slices), "ranged": bool(out.ranged), "passes": int(out.passes)}
+    return {"slices": list(out.slices), "ranged": bool(out.ranged), "passes": int(out.passes), "cluster": int(out.cluster)}
 
 
 class Profile(ctypes.Structure):
@@ -87,7 +90,8 @@ class Profile(ctypes.Structure):
                 ("rows_counted", ctypes.c_int64), ("alg_bytes", ctypes.c_int64),
                 ("class_ms", ctypes.c_double * 4), ("class_launches", ctypes.c_int64 * 4),
                 ("class_families", ctypes.c_int64 * 4), ("class_alg_bytes", ctypes.c_int64 * 4),
-                ("families_derived", ctypes.c_int64)]
+                ("families_derived", ctypes.c_int64), ("exchange_ms", ctypes.c_double),
+                ("exchange_bytes", ctypes.c_int64)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -125,6 +129,9 @@ def lib() -> ctypes.CDLL:
     L.bic_last_error.argtypes = [vp]
     L.bic_last_error.restype = ctypes.c_char_p
     L.bic_set_stream.argtypes = [vp, vp]
+    L.bic_wait_stream.argtypes = [vp, vp]
+    L.bic_dataset_fingerprint.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+    L.bic_score_dags_wire16.argtypes = [vp, vp, vp, i32, i64, ctypes.c_int, vp, ctypes.POINTER(i64), ctypes.c_int]
     L.bic_sync.argtypes = [vp]
     L.bic_set_iss.argtypes = [vp, ctypes.c_double]
     L.bic_set_dataset.argtypes = [vp, vp, i64, i32, i64, vp, ctypes.c_int]

@@ -26,7 +26,7 @@ using namespace bic;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // bic_last_error(NULL): last bic_create failure of the calling thread
 
 struct DevBuf {
     void *p = nullptr;
@@ -36,7 +36,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = bytes + bytes / 2 + 256;   // growth must be rare: cudaFree + cudaMalloc take milliseconds
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; return e; }
         cap = want;
@@ -58,6 +58,7 @@ struct NcclApi {
     int (*GetUniqueId)(nccl_uid *) = nullptr;
     int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
     int (*CommDestroy)(nccl_comm) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     std::string err;
@@ -72,9 +73,10 @@ struct NcclApi {
         GetUniqueId = (int (*)(nccl_uid *))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (int (*)(nccl_comm *, int, nccl_uid, int))dlsym(lib, "ncclCommInitRank");
         AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        AllGather = (int (*)(const void *, void *, size_t, int, nccl_comm, cudaStream_t))dlsym(lib, "ncclAllGather");
         CommDestroy = (int (*)(nccl_comm))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !AllGather || !CommDestroy) {
             err = "libnccl lacks a required symbol";
             lib = nullptr;
             return false;
@@ -84,7 +86,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 std::mutex g_nccl_mu;
-constexpr int NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;   // nccl.h: ncclDataType_t / ncclRedOp_t
+constexpr int NCCL_UINT8 = 1, NCCL_UINT32 = 3, NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;   // nccl.h: ncclDataType_t / ncclRedOp_t
 
 }  // namespace
 
@@ -94,7 +96,7 @@ struct bic_ctx {
     std::mutex mu;
     std::string err;
     int sm_count = 148;
-    size_t attr_smem[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
+    size_t attr_smem[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // opt-in dynamic shared memory already set per k_count instance
 
     // dataset
     uint8_t *data = nullptr;
@@ -117,7 +119,7 @@ struct bic_ctx {
 
     // per-sub-batch workspace
     DevBuf keybuf, inst, flag, rank, bsum32, bsum64, cells_arr, class_jobs, need, table_off, done, arena;
-    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_best, derived_list, derived_sorted;
+    DevBuf dag_bad, in_stage, in_stage2, in_stage3, in_stage4, out_stage, tmp_ll, donor, donor_best, derived_list, derived_sorted, owner, xoff, fp_buf;
     // Tuning knobs.  Defaults are the values swept on B200; the BIC_*
     // environment variables exist for those sweeps and for tests, not as a supported interface.
     struct Tuning {
@@ -132,7 +134,14 @@ struct bic_ctx {
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
                                                //   are counted in passes (0: always straight into HBM with L2 atomics)
         int class2_threads = 1024;             // BIC_CLASS2_THREADS: 512 or 1024 (classes 2 and 3-in-passes: one CTA per SM)
-        bool fma_extract = false;              // BIC_FMA_EXTRACT=1: packed path splits its 16-bit lanes on the FMA pipe (experiment)
+        int p2_vec = 4;                        // BIC_P2_VEC: 32-bit words of a packed column per thread-iteration (4, 2 or 1)
+        int cluster = 1;                       // BIC_CLUSTER=0: class 3 in sub-range passes instead of one pass over a thread-block cluster
+        int cluster_size = 0;                  // BIC_CLUSTER_SIZE: force 2, 4 or 8 CTAs per cluster (0: smallest that holds the table)
+        int cluster_threads = 1024;            // BIC_CLUSTER_THREADS: 512 or 1024
+        bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
+                                               //   fused reduce-scatter over peer memory
+        long long xchg_mb = 64;                // BIC_XCHG_MB: exchange-buffer slot per source rank (MB)
+        bool push_world1 = false;              // BIC_PUSH_WORLD1=1 (tests): a one-rank communicator also takes the exchange-buffer path
         bool fast_small = true;                // BIC_NO_FAST_SMALL=1: small warm batches take the general pipeline too
         bool slice_model = true;               // BIC_SLICE_MODEL=0: always cut the rows into L2 windows (round-1 versions a-h)
         void from_env() {
@@ -141,13 +150,19 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
             if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
             if (const char *e = getenv("BIC_L2_WINDOW_MAX_MB")) { long long mb = atoll(e); if (mb > 0) l2_window_max = mb << 20; }
-            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16383) class0_words = (u32)w; }
+            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16384) class0_words = (u32)w; }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
-            if (const char *e = getenv("BIC_FMA_EXTRACT")) fma_extract = atoi(e) != 0;
+            if (const char *e = getenv("BIC_P2_VEC")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) p2_vec = v; }
+            if (const char *e = getenv("BIC_CLUSTER")) cluster = atoi(e) != 0;
+            if (const char *e = getenv("BIC_CLUSTER_SIZE")) { int v = atoi(e); if (v == 0 || v == 2 || v == 4 || v == 8) cluster_size = v; }
+            if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
+            if (const char *e = getenv("BIC_NO_PUSH")) push = atoi(e) == 0;
+            if (const char *e = getenv("BIC_PUSH_WORLD1")) push_world1 = atoi(e) != 0;
+            if (const char *e = getenv("BIC_XCHG_MB")) { long long v = atoll(e); if (v > 0 && v <= 4096) xchg_mb = v; }
             if (const char *e = getenv("BIC_NO_FAST_SMALL")) fast_small = atoi(e) == 0;
             if (const char *e = getenv("BIC_SLICE_MODEL")) slice_model = atoi(e) != 0;
-            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) class0_threads = t; }
+            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) class0_threads = t; }
         }
     } tune;
     Header *d_hdr = nullptr, *h_hdr = nullptr;
@@ -163,6 +178,16 @@ struct bic_ctx {
     int rank_id = 0, world = 1;
     int comm_mode = 0;       // BIC_SHARD_ROWS or BIC_SHARD_FAMILIES
     bool ntotal_dirty = true;
+    // fused reduce-scatter of row-sharded count tables: every rank owns `world` slots of xcap cells;
+    // slot r of rank o receives rank r's partial tables of the families o owns (peer stores over NVLink)
+    u32 *xchg = nullptr;                 // this rank's exchange buffer (cudaMalloc, IPC-exported)
+    u64 xcap = 0;                        // cells per slot
+    std::vector<void *> peer_open;       // peers' buffers opened with cudaIpcOpenMemHandle (to close)
+    u32 **d_peer = nullptr;              // device array [world] of exchange-buffer pointers (own buffer at [rank])
+    int xchg_state = 0;                  // 0 not tried, 1 ready, -1 unavailable (fall back to ncclAllReduce of the tables)
+    int *d_barrier = nullptr;            // 4 bytes all-reduced as the "all pushes have landed" barrier
+    DevBuf terms, gkeys, gbad;           // staged family terms (one all-reduce), all-gathered keys / reject flags
+    cudaEvent_t ev_wait = nullptr;       // bic_wait_stream
     bool fast_ok = true;     // small warm batches: try k_score_small first (off after a miss, on again after an all-hit call)
 };
 
@@ -186,6 +211,13 @@ int fail(bic_ctx *c, int code, const std::string &msg) {
         int rc_ = (call);                 \
         if (rc_ != BIC_OK) return rc_;    \
     } while (0)
+
+inline u64 mix_host(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
 
 inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -239,15 +271,22 @@ int cache_ensure(bic_ctx *c, long long extra) {
         if (nnp) cudaFree(nnp);
         return fail(c, BIC_ERR_OOM, "device allocation for the family cache failed");
     }
-    CU(cudaMemsetAsync(ntable, 0, cap * sizeof(u32), c->stream));
-    if (c->reg_count) {
-        CU(cudaMemcpyAsync(nkeys, c->regkeys, (size_t)c->reg_count * c->Wk * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(nll, c->reg_ll, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(nnp, c->reg_np, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        k_rehash<<<nblk(c->reg_count, 256), 256, 0, c->stream>>>(nkeys, c->Wk, c->reg_count, ntable, (u32)(cap - 1)); LAUNCH(c);
-        CU(cudaGetLastError());
+    // fill the new allocation; on any failure it is released and the old cache stays in place
+    cudaError_t e = cudaMemsetAsync(ntable, 0, cap * sizeof(u32), c->stream);
+    if (e == cudaSuccess && c->reg_count) {
+        e = cudaMemcpyAsync(nkeys, c->regkeys, (size_t)c->reg_count * c->Wk * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nll, c->reg_ll, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nnp, c->reg_np, (size_t)c->reg_count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) {
+            k_rehash<<<nblk(c->reg_count, 256), 256, 0, c->stream>>>(nkeys, c->Wk, c->reg_count, ntable, (u32)(cap - 1)); LAUNCH(c);
+            e = cudaGetLastError();
+        }
     }
-    CU(cudaStreamSynchronize(c->stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        cudaFree(ntable); cudaFree(nkeys); cudaFree(nll); cudaFree(nnp);
+        return fail(c, BIC_ERR_CUDA, std::string("growing the family cache: ") + cudaGetErrorString(e));
+    }
     long long keep = c->reg_count;
     cache_free(c);
     c->table = ntable; c->regkeys = nkeys; c->reg_ll = nll; c->reg_np = nnp;
@@ -284,7 +323,7 @@ int header_fetch(bic_ctx *c) {
 // so far is remembered per context (= per device) and per template instance.
 template <int THREADS, bool GLOBAL, bool RANGE = false>
 int launch_count(bic_ctx *c, const CountArgs &a, long long items, size_t smem) {
-    size_t &attr_smem = c->attr_smem[RANGE ? (THREADS == 512 ? 7 : 8) : (THREADS == 128 ? 6 : THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
+    size_t &attr_smem = c->attr_smem[RANGE ? (THREADS == 512 ? 7 : 8) : (THREADS == 256 ? 0 : THREADS == 512 ? 1 : 2) + (GLOBAL ? 3 : 0)];
     if (smem > 40 * 1024 && smem > attr_smem) {   // static + dynamic over 48 KB needs the opt-in
         CU(cudaFuncSetAttribute(k_count<THREADS, GLOBAL, RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
@@ -308,6 +347,8 @@ int refresh_ntotal(bic_ctx *c) {
         CU(cudaMemcpyAsync(&c->N_total, d, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(d);
+        // the summed count tables are uint32 on the wire and int32 at the API
+        if (c->N_total >= (1ll << 31)) return fail(c, BIC_ERR_ARG, "row-sharded dataset holds 2^31 rows or more in total (int32 count tables)");
     }
     c->ntotal_dirty = false;
     return BIC_OK;
@@ -333,7 +374,16 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
     // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
     const long long span = CLASS2_CELLS;
     const int P3 = (int)((in.max_cells + span - 1) / span);
-    const bool ranged = in.class_count[3] > 0 && tune.range_passes > 0 && P3 <= tune.range_passes &&
+    // One pass over a thread-block cluster whose CTAs share the table (k_count_cluster) when it fits
+    // 8 x 192 KB of distributed shared memory; else sub-range passes; else (few rows) L2 atomics.
+    int CL = 0;
+    if (in.class_count[3] > 0 && tune.cluster && P3 <= 8 && in.N >= 4ll * in.max_cells) {
+        CL = 2;
+        while (CL < P3) CL *= 2;
+        if (tune.cluster_size > CL) CL = tune.cluster_size;
+    }
+    out.cluster = CL;
+    const bool ranged = CL == 0 && in.class_count[3] > 0 && tune.range_passes > 0 && P3 <= tune.range_passes &&
                         in.N >= 4ll * in.max_cells;
     out.ranged = ranged ? 1 : 0;
     out.passes = ranged ? P3 : 1;
@@ -344,16 +394,18 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
             // (a): the slice count that minimises rounds x (rows per CTA + set-up) + merge traffic.
             // Whole rounds matter when a class keeps one CTA per SM: 297 CTAs on 148 SMs take
             // three rounds, not two.
-            const bool rng3 = k == 3 && ranged;
-            const long long ctas = cnt * (rng3 ? P3 : 1);
+            const bool clu3 = k == 3 && CL > 0;
+            const bool rng3 = k == 3 && (ranged || clu3);   // one CTA per SM, rows >> cells
+            const long long ctas = cnt * (clu3 ? CL : rng3 ? P3 : 1);
             const long long slots = (long long)in.sm_count * (rng3 ? 1 : resident[k]);
             const long long hi = std::min(rng3 ? std::min(smax, in.N / (4ll * in.max_cells)) : smax,
                                           std::max<long long>(1, 4 * slots / ctas));
-            const double merge1 = (k == 3 && !ranged) ? 0.0 : (double)in.class_cells[k] / RED_PER_S;
+            const double merge1 = (k == 3 && !rng3) ? 0.0 : (double)in.class_cells[k] / RED_PER_S;
+            const double rowdiv = clu3 ? (double)CL : 1.0;   // the CTAs of a cluster share out the slice's rows
             double best = 0.0;
             for (long long s = 1; s <= hi; ++s) {
                 const double rounds = (double)((ctas * s + slots - 1) / slots);
-                const double t = rounds * (((double)in.N / (double)s) / CTA_ROWS_PER_S + CTA_SETUP_S) +
+                const double t = rounds * (((double)in.N / (double)s / rowdiv) / CTA_ROWS_PER_S + CTA_SETUP_S) +
                                  ((s > 1 || in.tables_in_hbm) ? (double)s * merge1 : 0.0);
                 if (s == 1 || t < best * 0.97) { best = t; S = s; }
             }
@@ -380,19 +432,131 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
     }
 }
 
+// Class 3 over a thread-block cluster: CL CTAs per (family, slice), one CTA per SM.
+template <int THREADS>
+int launch_count_cluster(bic_ctx *c, const CountArgs &a, long long items, int CL, size_t smem) {
+    size_t &attr_smem = c->attr_smem[THREADS == 512 ? 9 : 10];
+    if (smem > attr_smem) {
+        CU(cudaFuncSetAttribute(k_count_cluster<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(items * CL));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k_count_cluster<THREADS>, a, CL)); LAUNCH(c);
+    ++c->prof.count_launches;
+    return BIC_OK;
+}
+
+std::string nccl_err(int rc) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"; }
+
+// Exchange buffers of the fused reduce-scatter (row-sharded runs, world > 1).  Collective: every
+// rank allocates world slots, exports the allocation with cudaIpcGetMemHandle, the handles travel
+// with ncclAllGather and every peer's buffer is mapped with cudaIpcOpenMemHandle (which also enables
+// peer access).  Any failure on any rank (all-reduce of the outcome) leaves every rank on the
+// ncclAllReduce path.
+int xchg_setup(bic_ctx *c) {
+    if (c->xchg_state != 0) return BIC_OK;
+    c->xchg_state = -1;
+    if (!c->tune.push || (c->world < 2 && !c->tune.push_world1)) return BIC_OK;
+    const int W = c->world;
+    int ok = 1;
+    c->xcap = (u64)(c->tune.xchg_mb << 20) / sizeof(u32);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&c->xchg, (size_t)W * c->xcap * sizeof(u32)) != cudaSuccess) { c->xchg = nullptr; ok = 0; }
+    if (ok && cudaIpcGetMemHandle(&mine, c->xchg) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    // handles + outcome flags of every rank
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    uint8_t *d_all = nullptr;
+    std::vector<uint8_t> h_all((size_t)W * rec, 0);
+    CU(cudaMalloc(&d_all, (size_t)W * rec));
+    memcpy(h_all.data() + (size_t)c->rank_id * rec, &mine, sizeof(mine));
+    h_all[(size_t)c->rank_id * rec + sizeof(mine)] = (uint8_t)ok;
+    CU(cudaMemcpyAsync(d_all + (size_t)c->rank_id * rec, h_all.data() + (size_t)c->rank_id * rec, rec, cudaMemcpyHostToDevice, c->stream));
+    int rc = g_nccl.AllGather(d_all + (size_t)c->rank_id * rec, d_all, rec, NCCL_UINT8, c->comm, c->stream);
+    if (rc != 0) { cudaFree(d_all); return fail(c, BIC_ERR_NCCL, "ncclAllGather(exchange-buffer handles): " + nccl_err(rc)); }
+    CU(cudaMemcpyAsync(h_all.data(), d_all, (size_t)W * rec, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < W; ++r) ok = ok && h_all[(size_t)r * rec + sizeof(mine)];
+    std::vector<u32 *> peers((size_t)W, nullptr);
+    if (ok) {
+        for (int r = 0; r < W && ok; ++r) {
+            if (r == c->rank_id) { peers[r] = c->xchg; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, h_all.data() + (size_t)r * rec, sizeof(h));
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            c->peer_open.push_back(ptr);
+            peers[r] = (u32 *)ptr;
+        }
+    }
+    // second round: did every rank map every peer?
+    int *d_flag = nullptr;
+    CU(cudaMalloc(&d_flag, sizeof(int)));
+    CU(cudaMemcpyAsync(d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    rc = g_nccl.AllReduce(d_flag, d_flag, 1, NCCL_UINT32, NCCL_MIN, c->comm, c->stream);
+    int all_ok = 0;
+    if (rc == 0) {
+        CU(cudaMemcpyAsync(&all_ok, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(d_flag);
+    cudaFree(d_all);
+    if (rc != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(exchange-buffer outcome): " + nccl_err(rc));
+    if (!all_ok) {   // stay on the ncclAllReduce path
+        for (void *ptr : c->peer_open) cudaIpcCloseMemHandle(ptr);
+        c->peer_open.clear();
+        if (c->xchg) { cudaFree(c->xchg); c->xchg = nullptr; }
+        return BIC_OK;
+    }
+    CU(cudaMalloc(&c->d_peer, (size_t)W * sizeof(u32 *)));
+    CU(cudaMemcpy(c->d_peer, peers.data(), (size_t)W * sizeof(u32 *), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_barrier, sizeof(int)));
+    CU(cudaMemset(c->d_barrier, 0, sizeof(int)));
+    c->xchg_state = 1;
+    return BIC_OK;
+}
+
+void xchg_release(bic_ctx *c) {
+    for (void *ptr : c->peer_open) cudaIpcCloseMemHandle(ptr);
+    c->peer_open.clear();
+    if (c->xchg) cudaFree(c->xchg);
+    if (c->d_peer) cudaFree(c->d_peer);
+    if (c->d_barrier) cudaFree(c->d_barrier);
+    c->xchg = nullptr; c->d_peer = nullptr; c->d_barrier = nullptr;
+    c->xchg_state = 0;
+}
+
+struct RunOut {          // where run_count() writes the family terms
+    double *ll, *np;
+    long long base;      // index of job 0
+};
+
 // Count (and reduce) `njobs` families described in c->cells_arr / c->class_jobs; the header in
 // pinned memory holds the class counts.  keys/key_base select registry or key buffer.
+// push: row-sharded with the fused reduce-scatter (c->owner / c->xoff describe the jobs).
 int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, long long max_jobs,
-              double *ll_out, double *np_out, bool want_tables, bool with_donors) {
+              RunOut out, bool want_tables, bool with_donors, bool push) {
     const Header &h = *c->h_hdr;
     const bool sharded = c->comm != nullptr && c->comm_mode == BIC_SHARD_ROWS;
     const u32 n_derived = with_donors ? h.n_derived : 0;
     const u32 max_cells = h.max_cells;
     u32 lvl_count[DERIVE_LEVELS];
-    for (int l = 0; l < DERIVE_LEVELS; ++l) lvl_count[l] = with_donors ? h.lvl_count[l] : 0;   // header is re-fetched below
-    const bool all_tables = want_tables || sharded || n_derived > 0;
+    for (int l = 0; l < DERIVE_LEVELS; ++l) lvl_count[l] = with_donors ? h.lvl_count[l] : 0;
+    const bool all_tables = want_tables || (sharded && !push) || n_derived > 0;
 
-    // Row slices per family and how class 3 is counted: plan_count() below.
+    // Row slices per family and how class 3 is counted: plan_count() above.
     NeedArgs na;
     na.all = all_tables ? 1 : 0;
     bic_plan_in_t pin;
@@ -407,6 +571,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     const u32 span = CLASS2_CELLS;
     const int P3 = plan.passes;
     const bool ranged = plan.ranged != 0;
+    const int CL = plan.cluster;
     bool any_table = all_tables;
     for (int k = 0; k < NCLASS; ++k) {
         na.S[k] = plan.slices[k];
@@ -427,7 +592,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     CU(c->done.ensure((size_t)njobs * sizeof(u32)));
     CU(cudaMemsetAsync(c->done.p, 0, (size_t)njobs * sizeof(u32), c->stream));
 
-    CountArgs a;
+    CountArgs a = {};
     a.data = c->data; a.N = c->N; a.stride = c->stride; a.card = c->d_card; a.W64 = c->W64;
     a.data2 = c->data2; a.stride2 = c->stride2;
     a.keys = keys; a.key_base = key_base;
@@ -435,12 +600,19 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.need = any_table ? c->need.as<u32>() : nullptr;
     a.table_off = any_table ? c->table_off.as<u64>() : nullptr;
     a.done = c->done.as<u32>();
-    a.ll_out = ll_out; a.np_out = np_out;
+    a.ll_out = out.ll; a.np_out = out.np; a.out_base = out.base;
     a.reduce = sharded ? 0 : 1;
     a.donor = (with_donors && n_derived) ? c->donor.as<int>() : nullptr;
     a.bd_mode = c->cache_mode;
-    a.fma_extract = c->tune.fma_extract ? 1 : 0;
+    a.p2_vec = c->tune.p2_vec;
     a.iss = c->iss;
+    a.push = push ? 1 : 0;
+    a.rank = c->rank_id; a.world = c->world;
+    a.owner = push ? c->owner.as<int>() : nullptr;
+    a.xoff = push ? c->xoff.as<u64>() : nullptr;
+    a.peer = push ? c->d_peer : nullptr;
+    a.xcap = c->xcap;
+    a.writeback = (push && n_derived > 0) ? 1 : 0;
     u32 class_count[NCLASS];
     u64 class_alg[NCLASS];
     for (int k = 0; k < NCLASS; ++k) { class_count[k] = h.class_count[k]; class_alg[k] = h.alg_bytes[k]; }
@@ -451,10 +623,11 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         a.jobs = c->class_jobs.as<int>() + (long long)k * max_jobs;
         a.S = na.S[k];
         a.njobs = (int)cnt;
+        const bool clustered = k == 3 && CL > 0;
         a.P = (k == 3 && ranged) ? P3 : 1;
         a.span = span;
         long long items = cnt * a.S * a.P;
-        if (items > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
+        if (items * (clustered ? CL : 1) > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
         bic_ctx::EvPair ev = {nullptr, nullptr, k};
         if (c->prof_on) {   // CUDA events on the launching stream, one pair per count launch
             if (c->ev_pool.empty()) {
@@ -467,17 +640,14 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
             }
             CU(cudaEventRecord(ev.a, c->stream));
         }
-        // shared memory per CTA: class 0 gets 4x its largest table so that tables <= 256 cells
-        // run with 32 bank-interleaved lane replicas (conflict-free atomics).  Measured: giving
-        // mid-size tables (257..3072 cells) 112 KB x 2 CTAs or 192 KB x 1 CTA for replicas is
-        // SLOWER (7.2 vs 5.8 us per family at 10 M rows): with ~224 KB of the SM carved out as
-        // shared memory too little L1 is left to land the in-flight streaming loads.
+        // shared memory per CTA: class 0 gets several times its largest table so that small tables
+        // run with 32 or 16 bank-interleaved lane replicas (conflict-free atomics).
         const int c0t = c->tune.class0_threads;
         const u32 cap[NCLASS] = {c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
         const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
-        a.stage_words = k == 3 ? (ranged ? span : GLOBAL_STAGE) : cap[k];
-        if (k == 0 && c0t == 128) TRY((launch_count<128, false>(c, a, items, cap[0] * sizeof(u32))));
+        const u32 clwords = clustered ? (u32)((max_cells + CL - 1) / CL) : 0;
+        a.stage_words = k == 3 ? (clustered ? clwords : ranged ? span : GLOBAL_STAGE) : cap[k];
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
         if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));
@@ -485,7 +655,9 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         const bool wide = c->tune.class2_threads == 1024;
         if (k == 2 && !wide) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 2 && wide) TRY((launch_count<1024, false>(c, a, items, cap[2] * sizeof(u32))));
-        if (k == 3 && !ranged) TRY((launch_count<256, true>(c, a, items, GLOBAL_STAGE * sizeof(u32))));
+        if (k == 3 && clustered && c->tune.cluster_threads == 512) TRY((launch_count_cluster<512>(c, a, items, CL, clwords * sizeof(u32))));
+        if (k == 3 && clustered && c->tune.cluster_threads != 512) TRY((launch_count_cluster<1024>(c, a, items, CL, clwords * sizeof(u32))));
+        if (k == 3 && !clustered && !ranged) TRY((launch_count<256, true>(c, a, items, GLOBAL_STAGE * sizeof(u32))));
         if (k == 3 && ranged && !wide) TRY((launch_count<512, false, true>(c, a, items, span * sizeof(u32))));
         if (k == 3 && ranged && wide) TRY((launch_count<1024, false, true>(c, a, items, span * sizeof(u32))));
         if (c->prof_on) {
@@ -504,13 +676,35 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     c->prof.families_derived += n_derived;
 
     if (sharded) {
-        size_t cells = (size_t)h.cells_all;   // all tables live in HBM when sharded: exact
-        if (cells) {
-            int rc = g_nccl.AllReduce(c->arena.p, c->arena.p, cells, NCCL_UINT32, NCCL_SUM, c->comm, c->stream);
-            if (rc != 0) return fail(c, BIC_ERR_NCCL, std::string("ncclAllReduce(count tables): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        bic_ctx::EvPair ev = {nullptr, nullptr, -1};   // cls -1: the exchange step (collective + owner reduce)
+        if (c->prof_on) {
+            if (c->ev_pool.empty()) { CU(cudaEventCreate(&ev.a)); CU(cudaEventCreate(&ev.b)); }
+            else { ev = c->ev_pool.back(); ev.cls = -1; c->ev_pool.pop_back(); }
+            CU(cudaEventRecord(ev.a, c->stream));
+        }
+        if (push) {
+            // The count kernels have already stored every partial table into its owner's exchange
+            // buffer.  A 4-byte all-reduce orders "all ranks' count kernels are complete" before the
+            // owners read their slots; the owner then sums the world slots inside the fp64 reduce.
+            int rc = g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, NCCL_UINT32, NCCL_SUM, c->comm, c->stream);
+            if (rc != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(push barrier): " + nccl_err(rc));
+            long long counted_cells = 0;
+            for (int k = 0; k < NCLASS; ++k) counted_cells += (long long)h.class_cells[k];
+            c->prof.exchange_bytes += counted_cells * 4 * (c->world - 1) / c->world;   // what this rank stores into peers' buffers
+        } else {
+            size_t cells = (size_t)h.cells_all;   // all tables live in HBM when sharded: exact
+            if (cells) {
+                int rc = g_nccl.AllReduce(c->arena.p, c->arena.p, cells, NCCL_UINT32, NCCL_SUM, c->comm, c->stream);
+                if (rc != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(count tables): " + nccl_err(rc));
+            }
+            c->prof.exchange_bytes += (long long)cells * 4;
         }
         k_reduce_tables<256><<<(unsigned)njobs, 256, 0, c->stream>>>(a, (int)njobs); LAUNCH(c);
         CU(cudaGetLastError());
+        if (c->prof_on) {
+            CU(cudaEventRecord(ev.b, c->stream));
+            c->ev_used.push_back(ev);
+        }
     }
     if (n_derived) {   // tables of the counted families are complete: marginalise, most parents first
         // chunks per family: one per 4096 donor cells, as many as the largest table of the batch can need
@@ -538,12 +732,33 @@ int check_header_err(bic_ctx *c) {
 // keys of T instances sit in c->keybuf: look them up, insert + count the unseen families.
 int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     const bool famshard = c->comm != nullptr && c->comm_mode == BIC_SHARD_FAMILIES && c->world > 1;
+    const bool rowshard = c->comm != nullptr && c->comm_mode == BIC_SHARD_ROWS;
+    // Every allocation happens before k_probe: from there to the end a failure would leave PENDING
+    // entries or ids without terms in the table, so any non-OK return below drops the cache.
     TRY(cache_ensure(c, T));
     CU(c->inst.ensure((size_t)T * sizeof(int)));
     CU(c->flag.ensure((size_t)T * sizeof(u32)));
     CU(c->rank.ensure((size_t)T * sizeof(u32)));
     CU(c->cells_arr.ensure((size_t)T * sizeof(u32)));
     CU(c->class_jobs.ensure((size_t)T * NCLASS * sizeof(int)));
+    CU(c->donor.ensure((size_t)T * sizeof(int)));
+    CU(c->donor_best.ensure((size_t)T * sizeof(u64)));   // (joint cells, index) of the cheapest donor announced so far
+    CU(c->derived_list.ensure((size_t)T * sizeof(int)));
+    CU(c->derived_sorted.ensure((size_t)T * sizeof(int)));
+    CU(c->bsum32.ensure((size_t)((T + SCAN_CHUNK - 1) / SCAN_CHUNK + 1) * sizeof(u32)));
+    const bool multi = c->world > 1 || c->tune.push_world1;
+    if (rowshard && multi) {
+        TRY(xchg_setup(c));   // collective, first call only
+        CU(c->owner.ensure((size_t)T * sizeof(int)));
+        CU(c->xoff.ensure((size_t)T * sizeof(u64)));
+    }
+    const bool can_push = rowshard && multi && c->xchg_state == 1;
+    struct Guard {
+        bic_ctx *c;
+        bool armed;
+        ~Guard() { if (armed) cache_clear(c); }
+    } guard{c, true};
+
     unsigned g = nblk(T, 256);
     k_probe<<<g, 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->Wk, T, n_per_dag, c->dag_bad.as<uint8_t>(), c->table,
                                       (u32)(c->table_cap - 1), c->regkeys, c->inst.as<int>()); LAUNCH(c);
@@ -551,55 +766,69 @@ int resolve_instances(bic_ctx *c, long long T, int n_per_dag, bool no_derive) {
     TRY((scan_excl<u32, u32>(c, c->flag.as<u32>(), T, c->rank.as<u32>(), &c->d_hdr->f_new, c->bsum32)));
     k_finalize<<<g, 256, 0, c->stream>>>(c->keybuf.as<u64>(), c->Wk, T, c->inst.as<int>(), c->flag.as<u32>(),
                                          c->rank.as<u32>(), c->reg_count, c->regkeys, c->table); LAUNCH(c);
-    // new families: find superset donors (large datasets only), then describe / classify
-    CU(c->donor.ensure((size_t)T * sizeof(int)));
-    CU(c->donor_best.ensure((size_t)T * sizeof(u64)));   // (joint cells, index) of the cheapest donor announced so far
-    CU(c->derived_list.ensure((size_t)T * sizeof(int)));
-    CU(c->derived_sorted.ensure((size_t)T * sizeof(int)));
-    const int derive = (c->tune.derive && !no_derive && c->N >= c->tune.derive_min_rows) ? 1 : 0;
+    // New families: find superset donors (large datasets only), then describe / classify.  The
+    // decision to derive is taken from values every rank agrees on (row-sharded ranks hold shards
+    // that differ by a row: N_total / world, not the local N).
+    const long long rows_ref = rowshard ? c->N_total / std::max(1, c->world) : c->N;
+    const int derive = (c->tune.derive && !no_derive && rows_ref >= c->tune.derive_min_rows) ? 1 : 0;
     if (derive) {
         const int aw = famshard ? c->world : 1;
-        CU(cudaMemsetAsync(c->donor_best.p, 0xff, (size_t)T * sizeof(u64), c->stream));
-        k_announce<<<nblk(((T + aw - 1) / aw) * 32, 256), 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table,
-                                                                       (u32)(c->table_cap - 1), c->d_card, c->donor_best.as<u64>(),
-                                                                       famshard ? c->rank_id : 0, aw); LAUNCH(c);
-        if (famshard) {   // every rank announced for 1/world of the donors: combine the minima
-            int e = g_nccl.AllReduce(c->donor_best.p, c->donor_best.p, (size_t)T, NCCL_UINT64, NCCL_MIN, c->comm, c->stream);
-            if (e != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(donor search) failed");
+        long long fmax = T;   // upper bound of f_new
+        if (famshard) {       // one more header fetch buys an all-reduce over f_new instead of T entries
+            TRY(header_fetch(c));
+            fmax = c->h_hdr->f_new;
         }
+        if (fmax > 0) {
+            CU(cudaMemsetAsync(c->donor_best.p, 0xff, (size_t)fmax * sizeof(u64), c->stream));
+            k_announce<<<nblk(((fmax + aw - 1) / aw) * 32, 256), 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->table,
+                                                                              (u32)(c->table_cap - 1), c->d_card, c->donor_best.as<u64>(),
+                                                                              famshard ? c->rank_id : 0, aw); LAUNCH(c);
+            if (famshard) {   // every rank announced for 1/world of the donors: combine the minima
+                int e = g_nccl.AllReduce(c->donor_best.p, c->donor_best.p, (size_t)fmax, NCCL_UINT64, NCCL_MIN, c->comm, c->stream);
+                if (e != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(donor search): " + nccl_err(e));
+            }
+        }
+        k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c);
     }
-    if (derive) { k_pick_donor<<<g, 256, 0, c->stream>>>(c->donor_best.as<u64>(), c->d_hdr, derive, c->donor.as<int>()); LAUNCH(c); }
     k_describe_new<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_card, c->N, (u32)T, c->d_hdr,
                                              derive ? c->donor.as<int>() : nullptr, c->cells_arr.as<u32>(), c->class_jobs.as<int>(),
-                                             c->derived_list.as<int>(), c->rank_id, famshard ? c->world : 1); LAUNCH(c);
+                                             c->derived_list.as<int>(), c->rank_id, (famshard || can_push) ? c->world : 1,
+                                             famshard ? 1 : 0, can_push ? c->owner.as<int>() : nullptr); LAUNCH(c);
     if (derive) {
         k_group_derived<<<g, 256, 0, c->stream>>>(c->regkeys, c->W64, c->reg_count, c->d_hdr, c->derived_list.as<int>(),
                                                   c->derived_sorted.as<int>()); LAUNCH(c);
+    }
+    if (can_push) {
+        k_owner_offsets<<<c->world, 1024, 0, c->stream>>>(c->cells_arr.as<u32>(), c->owner.as<int>(),
+                                                          derive ? c->donor.as<int>() : nullptr, c->d_hdr, c->xoff.as<u64>()); LAUNCH(c);
     }
     CU(cudaGetLastError());
     TRY(header_fetch(c));
     long long f_new = c->h_hdr->f_new;
     c->lookups += T;
     c->misses += f_new;
-    int rc = check_header_err(c);
-    if (rc != BIC_OK) {   // new ids were published without scores: drop the whole cache
-        cache_clear(c);
-        return rc;
-    }
+    TRY(check_header_err(c));   // new ids were published without scores: the guard drops the whole cache
     if (f_new) {
-        if (famshard) {   // terms of the families other ranks own arrive through the all-reduce as x + 0 + ... + 0
-            CU(cudaMemsetAsync(c->reg_ll + c->reg_count, 0, (size_t)f_new * sizeof(double), c->stream));
-            CU(cudaMemsetAsync(c->reg_np + c->reg_count, 0, (size_t)f_new * sizeof(double), c->stream));
+        // push only when every rank's owned tables fit a slot of the exchange buffer (same header on every rank)
+        const bool push = can_push && c->h_hdr->owned_max <= c->xcap;
+        const bool staged = famshard || push;   // terms of the families other ranks own arrive as x + 0 + ... + 0
+        RunOut out = {c->reg_ll, c->reg_np, c->reg_count};
+        if (staged) {
+            CU(c->terms.ensure((size_t)f_new * 2 * sizeof(double)));
+            CU(cudaMemsetAsync(c->terms.p, 0, (size_t)f_new * 2 * sizeof(double), c->stream));
+            out = RunOut{c->terms.as<double>(), c->terms.as<double>() + f_new, 0};
         }
-        rc = run_count(c, c->regkeys, c->reg_count, f_new, T, c->reg_ll, c->reg_np, false, true);
-        if (rc == BIC_OK && famshard) {
-            int e1 = g_nccl.AllReduce(c->reg_ll + c->reg_count, c->reg_ll + c->reg_count, (size_t)f_new, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
-            int e2 = g_nccl.AllReduce(c->reg_np + c->reg_count, c->reg_np + c->reg_count, (size_t)f_new, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
-            if (e1 != 0 || e2 != 0) rc = fail(c, BIC_ERR_NCCL, "ncclAllReduce(family terms) failed");
+        TRY(run_count(c, c->regkeys, c->reg_count, f_new, T, out, false, true, push));
+        if (staged) {
+            int e = g_nccl.AllReduce(c->terms.p, c->terms.p, (size_t)f_new * 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            if (e != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(family terms): " + nccl_err(e));
+            CU(cudaMemcpyAsync(c->reg_ll + c->reg_count, c->terms.p, (size_t)f_new * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->reg_np + c->reg_count, c->terms.as<double>() + f_new, (size_t)f_new * sizeof(double),
+                               cudaMemcpyDeviceToDevice, c->stream));
         }
-        if (rc != BIC_OK) { cache_clear(c); return rc; }
         c->reg_count += f_new;
     }
+    guard.armed = false;
     return BIC_OK;
 }
 
@@ -609,8 +838,12 @@ int finish_call(bic_ctx *c) {
     for (auto &p : c->ev_used) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
-            c->prof.count_ms += ms;
-            c->prof.class_ms[p.cls] += ms;
+            if (p.cls < 0) {
+                c->prof.exchange_ms += ms;
+            } else {
+                c->prof.count_ms += ms;
+                c->prof.class_ms[p.cls] += ms;
+            }
         }
         c->ev_pool.push_back(p);
     }
@@ -648,17 +881,28 @@ long long sub_batch_dags(bic_ctx *c) {
     return std::max<long long>(1, max_inst / c->n);
 }
 
-enum DagFormat { FMT_ADJ, FMT_CSR, FMT_WIRE };
+enum DagFormat { FMT_ADJ, FMT_CSR, FMT_WIRE, FMT_WIRE16 };
 
+// ewords: FMT_WIRE16 only, 32-bit edge words per vertex.
 int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_t B, int metric, double *out,
-               int64_t *n_invalid, int flags) {
+               int64_t *n_invalid, int flags, int ewords = 1) {
     if (!c) return BIC_ERR_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     TRY(begin_call(c, metric, true));
     if (B < 0 || (B > 0 && (!p0 || !out))) return fail(c, BIC_ERR_ARG, "null pointer or negative batch size");
-    if (fmt == FMT_WIRE && c->n > 32) return fail(c, BIC_ERR_ARG, "wire format supports n <= 32");
+    if (fmt == FMT_WIRE && c->n > 32) return fail(c, BIC_ERR_ARG, "bic_score_dags_wire supports n <= 32; use bic_score_dags_wire16");
+    if (fmt == FMT_WIRE16 && ewords < (c->n + 31) / 32) return fail(c, BIC_ERR_ARG, "ewords < ceil(n / 32)");
+    const bool famshard = c->comm != nullptr && c->comm_mode == BIC_SHARD_FAMILIES && c->world > 1;
+    // BIC_FLAG_LOCAL_BATCH (family sharding): the arrays hold THIS rank's B DAGs (same B on every
+    // rank).  Keys are built and cycles checked locally, the keys travel with ncclAllGather over
+    // NVLink (16 bytes per family instead of n bytes of adjacency through every rank's PCIe link),
+    // the union is deduplicated identically on every rank and only the local scores come back.
+    const bool local = (flags & BIC_FLAG_LOCAL_BATCH) != 0;
+    if (local && !famshard) return fail(c, BIC_ERR_ARG, "BIC_FLAG_LOCAL_BATCH needs family sharding over more than one rank");
+    if (local && fmt == FMT_CSR && !(flags & BIC_FLAG_DEVICE_PTRS)) return fail(c, BIC_ERR_ARG, "BIC_FLAG_LOCAL_BATCH: CSR input must be device-resident");
     if (flags & BIC_FLAG_NO_CACHE) TRY(cache_clear(c));
     const int n = c->n;
+    const int W = local ? c->world : 1, R = local ? c->rank_id : 0;
     const double pen = metric_penalty(c, metric);
     const bool dev = (flags & BIC_FLAG_DEVICE_PTRS) != 0;
     long long invalid = 0;
@@ -687,19 +931,23 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
         c->fast_ok = false;   // a family is not cached yet: the general pipeline inserts and counts it
     }
     const long long misses0 = c->misses;
-    const long long Bs = sub_batch_dags(c);
+    const long long Bs = std::max<long long>(1, sub_batch_dags(c) / W);
     std::vector<long long> h_off;   // CSR offsets are needed on the host to slice a host batch
-    for (long long b0 = 0; b0 < B; b0 += Bs) {
-        long long Bc = std::min<long long>(Bs, B - b0);
-        long long T = Bc * n;
-        CU(c->keybuf.ensure((size_t)T * c->Wk * sizeof(u64)));
-        CU(c->dag_bad.ensure((size_t)Bc));
-        CU(cudaMemsetAsync(c->dag_bad.p, 0, (size_t)Bc, c->stream));
+    // B == 0 still takes part in the collectives of a local-batch call
+    for (long long b0 = 0; b0 < B || (local && b0 == 0); b0 += Bs) {
+        const long long Bc = std::min<long long>(Bs, B - b0);   // this rank's DAGs of the sub-batch
+        const long long Tl = Bc * n, T = Tl * W;                  // local / global family instances
+        CU(c->keybuf.ensure((size_t)std::max<long long>(T, 1) * c->Wk * sizeof(u64)));
+        CU(c->dag_bad.ensure((size_t)std::max<long long>(Bc * W, 1)));
+        u64 *lkeys = c->keybuf.as<u64>() + (size_t)R * Tl * c->Wk;   // this rank's part of the (global) key buffer
+        uint8_t *lbad = c->dag_bad.as<uint8_t>() + (size_t)R * Bc;
+        CU(cudaMemsetAsync(c->dag_bad.p, 0, (size_t)std::max<long long>(Bc * W, 1), c->stream));
         TRY(header_reset(c));
+        if (Bc > 0) {
         if (fmt == FMT_ADJ) {
             const uint8_t *adj = nullptr;
             TRY(stage_in(c, (const uint8_t *)p0 + b0 * (long long)n * n, (size_t)Bc * n * n, flags, c->in_stage, &adj));
-            k_keys_adj<<<nblk(T, 256), 256, 0, c->stream>>>(adj, Bc, n, c->W64, c->keybuf.as<u64>(), c->dag_bad.as<uint8_t>()); LAUNCH(c);
+            k_keys_adj<<<nblk(Tl, 256), 256, 0, c->stream>>>(adj, Bc, n, c->W64, lkeys, lbad); LAUNCH(c);
         } else if (fmt == FMT_CSR) {
             const long long *off = (const long long *)p0 + b0 * n;
             const int *par = (const int *)p1;
@@ -709,45 +957,58 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
                 d_off = off;     // absolute offsets into the caller's device array
                 d_par = par;
             } else {
-                long long e0 = off[0], e1 = off[T];
+                long long e0 = off[0], e1 = off[Tl];
                 if (e1 < e0) return fail(c, BIC_ERR_ARG, "CSR offsets are not monotone");
-                h_off.resize((size_t)T + 1);
-                for (long long i = 0; i <= T; ++i) h_off[(size_t)i] = off[i] - e0;
-                TRY(stage_in(c, h_off.data(), (size_t)T + 1, 0, c->in_stage, &d_off));
+                h_off.resize((size_t)Tl + 1);
+                for (long long i = 0; i <= Tl; ++i) h_off[(size_t)i] = off[i] - e0;
+                TRY(stage_in(c, h_off.data(), (size_t)Tl + 1, 0, c->in_stage, &d_off));
                 TRY(stage_in(c, par + e0, (size_t)(e1 - e0), 0, c->in_stage2, &d_par));
                 CU(cudaStreamSynchronize(c->stream));   // h_off is reused by the next sub-batch
             }
-            k_keys_csr<<<nblk(T, 256), 256, 0, c->stream>>>(d_off, d_par, nullptr, T, n, c->W64, c->keybuf.as<u64>(),
-                                                            c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
-        } else {
+            k_keys_csr<<<nblk(Tl, 256), 256, 0, c->stream>>>(d_off, d_par, nullptr, Tl, n, c->W64, lkeys, lbad, c->d_hdr); LAUNCH(c);
+        } else if (fmt == FMT_WIRE) {
             const uint8_t *lab = nullptr;
             const u32 *eb = nullptr;
             TRY(stage_in(c, (const uint8_t *)p0 + b0 * n, (size_t)Bc * n, flags, c->in_stage, &lab));
             TRY(stage_in(c, (const u32 *)p1 + b0 * n, (size_t)Bc * n, flags, c->in_stage2, &eb));
-            k_keys_wire<<<nblk(Bc, 128), 128, 0, c->stream>>>(lab, eb, Bc, n, c->keybuf.as<u64>(), c->dag_bad.as<uint8_t>()); LAUNCH(c);
-        }
-        if ((flags & BIC_FLAG_NO_CYCLE_CHECK) || fmt == FMT_WIRE) {
-            k_count_bad<<<nblk(Bc, 256), 256, 0, c->stream>>>(c->dag_bad.as<uint8_t>(), Bc, c->d_hdr); LAUNCH(c);
+            k_keys_wire<uint8_t><<<nblk(Bc, 128), 128, 0, c->stream>>>(lab, eb, Bc, n, lkeys, lbad); LAUNCH(c);
         } else {
-            if (n > 128) k_acyclic<true><<<(unsigned)Bc, ACYC_WIDE_THREADS, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
-                                                                             c->dag_bad.as<uint8_t>(), c->d_hdr);
-            else k_acyclic<false><<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(c->keybuf.as<u64>(), Bc, n, c->W64,
-                                                                             c->dag_bad.as<uint8_t>(), c->d_hdr); LAUNCH(c);
+            const uint16_t *lab = nullptr;
+            const u32 *eb = nullptr;
+            TRY(stage_in(c, (const uint16_t *)p0 + b0 * n, (size_t)Bc * n, flags, c->in_stage, &lab));
+            TRY(stage_in(c, (const u32 *)p1 + b0 * n * (long long)ewords, (size_t)Bc * n * ewords, flags, c->in_stage2, &eb));
+            if (n <= 32 && ewords == 1) { k_keys_wire<uint16_t><<<nblk(Bc, 128), 128, 0, c->stream>>>(lab, eb, Bc, n, lkeys, lbad); LAUNCH(c); }
+            else { k_keys_wire_wide<<<(unsigned)Bc, WIRE_WIDE_THREADS, 0, c->stream>>>(lab, eb, Bc, n, ewords, c->W64, lkeys, lbad); LAUNCH(c); }
+        }
+        if ((flags & BIC_FLAG_NO_CYCLE_CHECK) || fmt == FMT_WIRE || fmt == FMT_WIRE16) {
+            k_count_bad<<<nblk(Bc, 256), 256, 0, c->stream>>>(lbad, Bc, c->d_hdr); LAUNCH(c);
+        } else {
+            if (n > 128) k_acyclic<true><<<(unsigned)Bc, ACYC_WIDE_THREADS, 0, c->stream>>>(lkeys, Bc, n, c->W64, lbad, c->d_hdr);
+            else k_acyclic<false><<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(lkeys, Bc, n, c->W64, lbad, c->d_hdr);
+            LAUNCH(c);
         }
         CU(cudaGetLastError());
-        TRY(resolve_instances(c, T, n, (flags & BIC_FLAG_NO_DERIVE) != 0));
+        }
+        if (local) {   // in-place all-gather: every rank's keys / reject flags at its own offset
+            if (Tl > 0) {
+                int e1 = g_nccl.AllGather(lkeys, c->keybuf.p, (size_t)Tl * c->Wk * sizeof(u64), NCCL_UINT8, c->comm, c->stream);
+                int e2 = g_nccl.AllGather(lbad, c->dag_bad.p, (size_t)Bc, NCCL_UINT8, c->comm, c->stream);
+                if (e1 != 0 || e2 != 0) return fail(c, BIC_ERR_NCCL, "ncclAllGather(candidate keys): " + nccl_err(e1 ? e1 : e2));
+            }
+        }
+        if (T > 0) TRY(resolve_instances(c, T, n, (flags & BIC_FLAG_NO_DERIVE) != 0));
+        if (Bc <= 0) break;
         invalid += c->h_hdr->n_invalid;
         double *d_out = out + b0;
         if (!dev) {
             CU(c->out_stage.ensure((size_t)Bc * sizeof(double)));
             d_out = c->out_stage.as<double>();
         }
+        const int *linst = c->inst.as<int>() + (size_t)R * Tl;
         if (n >= 64)
-            k_gather_dags_warp<<<nblk(Bc * 32, 128), 128, 0, c->stream>>>(c->inst.as<int>(), c->table, Bc, n, c->dag_bad.as<uint8_t>(),
-                                                                          c->reg_ll, c->reg_np, pen, d_out);
+            k_gather_dags_warp<<<nblk(Bc * 32, 128), 128, 0, c->stream>>>(linst, c->table, Bc, n, lbad, c->reg_ll, c->reg_np, pen, d_out);
         else
-            k_gather_dags<<<nblk(Bc, 128), 128, 0, c->stream>>>(c->inst.as<int>(), c->table, Bc, n, c->dag_bad.as<uint8_t>(),
-                                                                c->reg_ll, c->reg_np, pen, d_out);
+            k_gather_dags<<<nblk(Bc, 128), 128, 0, c->stream>>>(linst, c->table, Bc, n, lbad, c->reg_ll, c->reg_np, pen, d_out);
         LAUNCH(c);
         CU(cudaGetLastError());
         if (!dev) CU(cudaMemcpyAsync(out + b0, d_out, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -812,12 +1073,14 @@ int bic_destroy(bic_ctx *c) {
     if (!c) return BIC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    xchg_release(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->ev_wait) cudaEventDestroy(c->ev_wait);
     cache_free(c);
     DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
                       &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
                       &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_best,
-                      &c->derived_list};
+                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
     if (c->data2) cudaFree(c->data2);
@@ -836,6 +1099,35 @@ int bic_set_stream(bic_ctx *c, void *cuda_stream) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return BIC_OK;
+}
+
+int bic_wait_stream(bic_ctx *c, void *producer_stream) {
+    if (!c) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    cudaStream_t ps = (cudaStream_t)producer_stream;   // NULL = the legacy default stream
+    if (ps == c->stream) return BIC_OK;
+    if (!c->ev_wait) CU(cudaEventCreateWithFlags(&c->ev_wait, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_wait, ps));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_wait, 0));
+    return BIC_OK;
+}
+
+int bic_dataset_fingerprint(bic_ctx *c, uint64_t *out) {
+    if (!c || !out) return BIC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->data) return fail(c, BIC_ERR_NO_DATASET, "no dataset: call bic_set_dataset first");
+    CU(cudaSetDevice(c->device));
+    CU(c->fp_buf.ensure(sizeof(u64)));
+    CU(cudaMemsetAsync(c->fp_buf.p, 0, sizeof(u64), c->stream));
+    dim3 grid((unsigned)std::min<long long>(1024, (c->N / 16 + 255) / 256 + 1), (unsigned)c->n);
+    k_fingerprint<<<grid, 256, 0, c->stream>>>(c->data, c->N, c->stride, c->n, c->fp_buf.as<u64>()); LAUNCH(c);
+    CU(cudaGetLastError());
+    u64 v = 0;
+    CU(cudaMemcpyAsync(&v, c->fp_buf.p, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = v ^ mix_host((u64)c->N * 0x9E3779B97F4A7C15ULL + (u64)c->n);
     return BIC_OK;
 }
 
@@ -887,7 +1179,7 @@ int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int6
     c->ntotal_dirty = true;
     // validate codes < card on the device
     TRY(header_reset(c));
-    dim3 grid((unsigned)std::min<long long>(1024, (N + 255) / 256), (unsigned)n);
+    dim3 grid((unsigned)std::min<long long>(1024, (N / 16 + 255) / 256 + 1), (unsigned)n);
     k_validate<<<grid, 256, 0, c->stream>>>(c->data, N, pstride, n, c->d_card, &c->d_hdr->err); LAUNCH(c);
     CU(cudaGetLastError());
     TRY(header_fetch(c));
@@ -949,7 +1241,7 @@ int bic_count_families(bic_ctx *c, const int32_t *node, const int64_t *parent_of
     CU(cudaGetLastError());
     TRY(header_fetch(c));
     TRY(check_header_err(c));
-    TRY(run_count(c, c->keybuf.as<u64>(), 0, F, F, c->tmp_ll.as<double>(), c->tmp_ll.as<double>() + F, true, false));
+    TRY(run_count(c, c->keybuf.as<u64>(), 0, F, F, RunOut{c->tmp_ll.as<double>(), c->tmp_ll.as<double>() + F, 0}, true, false, false));
     int *d_out = counts_out;
     if (!dev) {
         CU(c->out_stage.ensure((size_t)std::max<long long>(cells_total, 1) * sizeof(int)));
@@ -1024,6 +1316,13 @@ int bic_score_dags_wire(bic_ctx *c, const uint8_t *labels, const uint32_t *ebits
     return score_dags(c, FMT_WIRE, labels, ebits, B, metric, out, n_invalid, flags);
 }
 
+int bic_score_dags_wire16(bic_ctx *c, const uint16_t *labels, const uint32_t *ebits, int32_t ewords, int64_t B, int metric,
+                          double *out, int64_t *n_invalid, int flags) {
+    if (c && B > 0 && !ebits) return fail(c, BIC_ERR_ARG, "ebits is NULL");
+    if (c && ewords < 1) return fail(c, BIC_ERR_ARG, "ewords must be >= 1");
+    return score_dags(c, FMT_WIRE16, labels, ebits, B, metric, out, n_invalid, flags, ewords);
+}
+
 int bic_cache_clear(bic_ctx *c) {
     if (!c) return BIC_ERR_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1075,8 +1374,6 @@ int bic_cache_import(bic_ctx *c, const uint64_t *keys, const double *terms, cons
     if (!c->data) return fail(c, BIC_ERR_NO_DATASET, "no dataset: call bic_set_dataset first");
     if (families < 0 || kind < 0 || kind > 2 || (families > 0 && (!keys || !terms || !nparams)))
         return fail(c, BIC_ERR_ARG, "bad import arguments");
-    for (int64_t f = 0; f < families; ++f)
-        if (keys[f * c->Wk] >= (uint64_t)c->n) return fail(c, BIC_ERR_ARG, "imported key names a node outside the dataset");
     CU(cudaSetDevice(c->device));
     TRY(cache_clear(c));
     c->cache_mode = kind;
@@ -1085,9 +1382,17 @@ int bic_cache_import(bic_ctx *c, const uint64_t *keys, const double *terms, cons
     CU(cudaMemcpyAsync(c->regkeys, keys, (size_t)families * c->Wk * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->reg_ll, terms, (size_t)families * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->reg_np, nparams, (size_t)families * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_rehash<<<nblk(families, 256), 256, 0, c->stream>>>(c->regkeys, c->Wk, families, c->table, (u32)(c->table_cap - 1)); LAUNCH(c);
+    // keys are validated on the device: node and parent bits inside the dataset, no self parent, no key twice
+    TRY(header_reset(c));
+    k_check_keys<<<nblk(families, 256), 256, 0, c->stream>>>(c->regkeys, c->W64, families, c->n, &c->d_hdr->err); LAUNCH(c);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
+    TRY(header_fetch(c));
+    if (c->h_hdr->err) { cache_clear(c); return fail(c, BIC_ERR_ARG, "imported key names a node or parent outside the dataset, or a node as its own parent"); }
+    k_rehash<<<nblk(families, 256), 256, 0, c->stream>>>(c->regkeys, c->Wk, families, c->table, (u32)(c->table_cap - 1)); LAUNCH(c);
+    k_check_duplicates<<<nblk(families, 256), 256, 0, c->stream>>>(c->regkeys, c->Wk, families, c->table, (u32)(c->table_cap - 1), &c->d_hdr->err); LAUNCH(c);
+    CU(cudaGetLastError());
+    TRY(header_fetch(c));
+    if (c->h_hdr->err) { cache_clear(c); return fail(c, BIC_ERR_ARG, "imported keys hold the same family twice"); }
     c->reg_count = families;
     return BIC_OK;
 }
@@ -1133,6 +1438,7 @@ int bic_comm_init(bic_ctx *c, const uint8_t id[128], int rank, int world) {
         if (!g_nccl.load()) return fail(c, BIC_ERR_NCCL, g_nccl.err);
     }
     CU(cudaSetDevice(c->device));
+    xchg_release(c);
     if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     nccl_uid uid;
     memcpy(uid.internal, id, 128);
@@ -1164,6 +1470,7 @@ int bic_comm_destroy(bic_ctx *c) {
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    xchg_release(c);
     if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     c->world = 1; c->rank_id = 0;
     c->ntotal_dirty = true;

@@ -57,12 +57,14 @@ __global__ void k_keys_csr(const long long *__restrict__ off, const int *__restr
 // Reference wire format (src/toolkit/labeled.py:132-154): vertex v carries label l_v (= BN
 // variable), bit u of ebits[v] <=> edge vertex u -> vertex v, u < v.  bnlearn.py:38-42 relabels
 // vertices to variables; here one thread per DAG does that and writes the n keys in variable
-// order.  n <= 32, so one mask word.
-__global__ void k_keys_wire(const uint8_t *__restrict__ labels, const u32 *__restrict__ ebits,
+// order.  n <= 32, so one mask word.  LT: uint8 (legacy entry point) or uint16 (the reference's
+// own label type, labeled.py:118).
+template <typename LT>
+__global__ void k_keys_wire(const LT *__restrict__ labels, const u32 *__restrict__ ebits,
                             long long B, int n, u64 *keybuf, uint8_t *dag_bad) {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const uint8_t *lab = labels + b * n;
+    const LT *lab = labels + b * n;
     const u32 *eb = ebits + b * n;
     u32 seen = 0;
     for (int v = 0; v < n; ++v) {
@@ -86,6 +88,62 @@ __global__ void k_keys_wire(const uint8_t *__restrict__ labels, const u32 *__res
         long long t = b * n + lab[v];
         keybuf[t * 2] = (u64)lab[v];
         keybuf[t * 2 + 1] = m;
+    }
+}
+
+// The same for any n <= 1024 (alarm-shaped n = 37, pigs-shaped n = 441): uint16 labels, EW =
+// ceil(n / 32) edge words per vertex (bit u % 32 of word u / 32 of ebits[b][v] <=> edge u -> v).
+// One block per DAG: the labels and a seen-bitmap sit in shared memory, thread v builds the
+// parent mask of variable lab[v].
+constexpr int WIRE_WIDE_THREADS = 128;
+__global__ void __launch_bounds__(WIRE_WIDE_THREADS)
+k_keys_wire_wide(const uint16_t *__restrict__ labels, const u32 *__restrict__ ebits, long long B, int n, int EW,
+                 int W64, u64 *keybuf, uint8_t *dag_bad) {
+    __shared__ uint16_t s_lab[NMAX];
+    __shared__ u32 s_seen[NMAX / 32];
+    __shared__ int s_ok;
+    const long long b = blockIdx.x;
+    const int Wk = W64 + 1;
+    for (int w = threadIdx.x; w < NMAX / 32; w += blockDim.x) s_seen[w] = 0;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        const int l = labels[b * n + v];
+        s_lab[v] = (uint16_t)l;
+        if (l < n) {
+            if (atomicOr(&s_seen[l >> 5], 1u << (l & 31)) & (1u << (l & 31))) s_ok = 0;   // label used twice
+        } else {
+            s_ok = 0;
+        }
+    }
+    __syncthreads();
+    u64 *keys = keybuf + b * (long long)n * Wk;
+    if (!s_ok) {   // bnlearn.py:35 asserts the labels are exactly 0..n-1
+        if (threadIdx.x == 0) dag_bad[b] = 1;
+        for (int v = threadIdx.x; v < n; v += blockDim.x) {
+            keys[(long long)v * Wk] = (u64)v;
+            for (int w = 0; w < W64; ++w) keys[(long long)v * Wk + 1 + w] = 0;
+        }
+        return;
+    }
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        u64 m[W64MAX];
+        for (int w = 0; w < W64; ++w) m[w] = 0;
+        const u32 *eb = ebits + (b * n + v) * (long long)EW;
+        for (int ew = 0; ew * 32 < v; ++ew) {
+            u32 e = eb[ew];
+            const int left = v - ew * 32;               // only u < v count (labeled.py:143-145)
+            if (left < 32) e &= (1u << left) - 1u;
+            while (e) {
+                const int u = ew * 32 + __ffs(e) - 1;
+                e &= e - 1;
+                const int l = s_lab[u];
+                m[l >> 6] |= 1ull << (l & 63);
+            }
+        }
+        u64 *key = keys + (long long)s_lab[v] * Wk;
+        key[0] = (u64)s_lab[v];
+        for (int w = 0; w < W64; ++w) key[1 + w] = m[w];
     }
 }
 
@@ -434,21 +492,27 @@ __global__ void k_pick_donor(const u64 *__restrict__ best, const Header *hdr, in
 
 // Describe the new families: counted ones get a count job, derived ones go to the derive list.
 // donor == nullptr: derivation is off, every new family is counted.
-// world > 1 (family sharding): a family belongs to the rank that owns the root of its donor chain,
-// so a derived family and every table it is derived from live on the same rank; families of other
-// ranks get no job and no table here.
+// world > 1: a family belongs to the rank that owns the root of its donor chain, so a derived
+// family and every table it is derived from live on the same rank.  Family sharding (filter):
+// families of other ranks get no job and no table here.  Row sharding with the fused
+// reduce-scatter (owner_out): every rank counts every family on its rows, the owner reduces.
 __global__ void k_describe_new(const u64 *__restrict__ regkeys, int W64, long long base, const int *__restrict__ card,
                                long long N, u32 max_jobs, Header *hdr, const int *__restrict__ donor,
-                               u32 *cells_arr, int *class_jobs, int *derived_list, int rank, int world) {
+                               u32 *cells_arr, int *class_jobs, int *derived_list, int rank, int world,
+                               int filter, int *owner_out) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= hdr->f_new) return;
     if (world > 1) {
         long long root = j;
         while (donor && donor[root] >= 0) root = donor[root];
-        if ((int)(mix64((u64)root) % (u64)world) != rank) {
+        const int own = (int)(mix64((u64)root) % (u64)world);
+        if (owner_out) owner_out[j] = own;
+        if (filter && own != rank) {   // family sharding: another rank counts this family
             cells_arr[j] = 0;
             return;
         }
+    } else if (owner_out) {
+        owner_out[j] = 0;
     }
     const u64 *key = regkeys + (base + j) * (W64 + 1);
     if (!donor || donor[j] < 0) {
@@ -633,16 +697,97 @@ __global__ void k_gather_fams(const int *__restrict__ inst, const u32 *__restric
     out[t] = ll[id] - pen * np[id];
 }
 
+// Offsets of the new families inside a slot of their owner's exchange buffer (row-sharded runs
+// with the fused reduce-scatter): block w walks all jobs and packs those of owner w back to back
+// (derived families get no space: only counted tables travel).  hdr->owned_max = the largest
+// total, which must fit a slot.  Deterministic: every rank computes the same offsets.
+__global__ void __launch_bounds__(1024) k_owner_offsets(const u32 *__restrict__ cells_arr, const int *__restrict__ owner,
+                                                        const int *__restrict__ donor, Header *hdr, u64 *xoff) {
+    __shared__ u64 sh[1024];
+    __shared__ u64 carry;
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const u32 njobs = hdr->f_new;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < njobs; base += 1024) {
+        const u32 i = base + tid;
+        const bool mine = i < njobs && owner[i] == w && !(donor && donor[i] >= 0);
+        const u64 v = mine ? (u64)((cells_arr[i] + 3u) & ~3u) : 0ull;   // 16-byte aligned tables
+        sh[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            u64 x = (tid >= o) ? sh[tid - o] : 0ull;
+            __syncthreads();
+            sh[tid] += x;
+            __syncthreads();
+        }
+        const u64 incl = sh[tid], c = carry;
+        __syncthreads();
+        if (mine) xoff[i] = c + incl - v;
+        if (tid == 1023) carry = c + incl;
+        __syncthreads();
+    }
+    if (tid == 0) atomicMax(&hdr->owned_max, carry);
+}
+
 // ------------------------------------------------------------------- dataset validation
+// 16 rows per load; a byte >= card is found with per-byte compares on the four words.
 __global__ void k_validate(const uint8_t *__restrict__ data, long long N, long long stride, int n,
                            const int *__restrict__ card, u32 *bad) {
     int v = blockIdx.y;
-    int c = card[v];
-    const uint8_t *col = data + (long long)v * stride;
+    const u32 c = (u32)card[v];
+    const uint4 *col = reinterpret_cast<const uint4 *>(data + (long long)v * stride);
+    const long long nvec = (N + 15) >> 4;   // tail rows of the padded column hold state 0
     bool b = false;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x)
-        b = b || (col[r] >= c);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = col[i];
+        const u32 ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) b = b || (((ws[k] >> (8 * s)) & 0xffu) >= c);
+    }
     if (b) atomicOr(bad, 1u);
+}
+
+// 64-bit content fingerprint of the dataset (cache checkpoints refuse another dataset of the same
+// shape): order-independent sum of mixed (position, 16-row word) pairs.
+__global__ void k_fingerprint(const uint8_t *__restrict__ data, long long N, long long stride, int n, u64 *out) {
+    int v = blockIdx.y;
+    const uint4 *col = reinterpret_cast<const uint4 *>(data + (long long)v * stride);
+    const long long nvec = (N + 15) >> 4;
+    u64 acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = col[i];
+        const u64 pos = (u64)v * 0x9E3779B97F4A7C15ULL + (u64)i;
+        acc += mix64(pos ^ mix64(((u64)w.x << 32 | w.y) + 0x632BE59BD9B4E019ULL * (((u64)w.z << 32) | w.w)));
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// Imported cache keys (bic_cache_import): node < n, parent bits < n, node not its own parent.
+__global__ void k_check_keys(const u64 *__restrict__ keys, int W64, long long count, int n, u32 *bad) {
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    const u64 *key = keys + id * (W64 + 1);
+    bool b = key[0] >= (u64)n;
+    for (int w = 0; w < W64; ++w) {
+        const int bits = min(64, max(0, n - w * 64));
+        const u64 valid = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+        b = b || (key[1 + w] & ~valid);
+    }
+    if (!b) b = (key[1 + (key[0] >> 6)] >> (key[0] & 63)) & 1ull;
+    if (b) atomicOr(bad, 1u);
+}
+
+// After k_rehash of imported keys: a key present twice sits in two slots; the second lookup of its
+// own key finds the other id.
+__global__ void k_check_duplicates(const u64 *__restrict__ regkeys, int Wk, long long count, const u32 *__restrict__ table,
+                                   u32 mask, u32 *bad) {
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    if (cache_find(regkeys + id * Wk, Wk, table, mask, regkeys) != id) atomicOr(bad, 2u);
 }
 
 // ------------------------------------------------------------ 2-bit shadow copy of the dataset

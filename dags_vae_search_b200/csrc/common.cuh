@@ -40,6 +40,7 @@ struct Header {
     u32 n_derived;             // new families whose table is marginalised from a counted superset
     u32 lvl_count[DERIVE_LEVELS];   // of those, by number of parents
     u32 lvl_cursor[DERIVE_LEVELS];  // device scratch: fill positions while the derived families are grouped by level
+    u64 owned_max;             // row-sharded runs: most cells any one rank owns (must fit a slot of the exchange buffer)
 };
 
 __device__ __forceinline__ u64 mix64(u64 x) {

@@ -36,13 +36,24 @@ struct CountArgs {
     const u32 *need;         // per job: cells if its table lives in HBM, else 0 (nullable)
     const u64 *table_off;    // per job: offset into arena (valid where need != 0)
     u32 *done;               // per job: slice tickets
-    double *ll_out;          // [key_base + j]
-    double *np_out;          // [key_base + j]  (r - 1) * q
+    long long out_base;      // job j writes ll_out / np_out [out_base + j] (= key_base for the registry, 0 for staged terms)
+    double *ll_out;
+    double *np_out;          // (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
-    int fma_extract;         // packed path: split 16-bit lanes with IMAD.HI / IMAD instead of SHF / LOP3
+    int p2_vec;              // packed path: 32-bit words of a column one thread loads per iteration (4, 2 or 1)
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
     double iss;
+    // Row-sharded runs, fused count + reduce-scatter (push != 0): the CTA that completes a family's
+    // local table stores it into slot `rank` of the owner rank's exchange buffer over NVLink
+    // (peer[owner[j]] + rank * xcap + xoff[j]); the owner sums the `world` slots in k_reduce_tables.
+    int push;
+    int rank, world;
+    const int *owner;        // per job: rank that reduces (and derives from) the family's global table
+    const u64 *xoff;         // per job: cell offset inside a slot of the owner's exchange buffer
+    u32 *const *peer;        // [world] exchange buffers (peer-mapped device pointers; own buffer at [rank])
+    u64 xcap;                // cells per slot
+    int writeback;           // k_reduce_tables: also store the summed table into the local arena (donors of derived families)
 };
 
 struct FamMeta {
@@ -52,7 +63,6 @@ struct FamMeta {
     u32 R;      // lane replicas of the shared-memory table (power of two, <= 32)
     u32 mul;    // byte offset of a cell = cell * mul  (mul = 4 * R)
     u32 lo4, span4;   // RANGE kernel: byte offset of the CTA's first cell, bytes of its sub-range
-    u32 k16;    // 65536, opaque to the compiler: 16-bit lane extraction as IMAD.HI / IMAD (FMA pipe) instead of SHF / LOP3 (ALU pipe)
     int par[KMAX];
     u32 rad[KMAX];
 };
@@ -254,19 +264,40 @@ __device__ __forceinline__ void unpack2(u32 W, u32 (&u)[4]) {
     u[3] = (W >> 6) & 0x03030303u;
 }
 
-template <int K, bool MASKED, bool FMAX>
-__device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&rad)[K + 1], u32 mul, u32 plow_mul,
-                                         u32 *hist, int lim, u32 k16) {
+// VEC = 32-bit words (16 rows each) of every column a thread loads per iteration: 4 (one 128-bit
+// load = 64 rows), 2 or 1.  Fewer bytes in flight per thread leave more of the SM's unified
+// L1 / shared memory to the lane-replicated tables (the rows come from L2, so short loads still
+// cover the latency); the arithmetic per word is the same.
+template <int VEC> struct P2Load;
+template <> struct P2Load<4> {
+    static __device__ __forceinline__ void ld(const uint8_t *p, u32 (&w)[4]) {
+        uint4 r = ld_stream_v4(p);
+        w[0] = r.x; w[1] = r.y; w[2] = r.z; w[3] = r.w;
+    }
+};
+template <> struct P2Load<2> {
+    static __device__ __forceinline__ void ld(const uint8_t *p, u32 (&w)[2]) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+    }
+};
+template <> struct P2Load<1> {
+    static __device__ __forceinline__ void ld(const uint8_t *p, u32 (&w)[1]) {
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+    }
+};
+
+template <int K, int VEC, bool MASKED>
+__device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (&rad)[K + 1], u32 mul, u32 plow_mul,
+                                         u32 *hist, int lim) {
     constexpr int C = K + 1;                  // columns, child last
     constexpr int C1 = C > 4 ? C - 4 : 0;     // columns of the high group
 #pragma unroll
-    for (int wd = 0; wd < 4; ++wd) {
+    for (int wd = 0; wd < VEC; ++wd) {
         u32 hi[4], lo[4];
 #pragma unroll
         for (int a = 0; a < C; ++a) {
-            const u32 W = wd == 0 ? w[a].x : wd == 1 ? w[a].y : wd == 2 ? w[a].z : w[a].w;
             u32 u[4];
-            unpack2(W, u);
+            unpack2(w[a][wd], u);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 if (a < C1) hi[s] = (a == 0) ? u[s] : hi[s] * rad[a] + u[s];
@@ -281,15 +312,7 @@ __device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&ra
                 t01 += __byte_perm(hi[s], 0u, 0x4140u) * plow_mul;
                 t23 += __byte_perm(hi[s], 0u, 0x4342u) * plow_mul;
             }
-            u32 off[4];
-            if (FMAX) {   // the ALU pipe is the co-limiter (76 %): split the lanes on the FMA pipe
-                off[1] = __umulhi(t01, k16);
-                off[0] = t01 - off[1] * k16;
-                off[3] = __umulhi(t23, k16);
-                off[2] = t23 - off[3] * k16;
-            } else {
-                off[0] = t01 & 0xffffu; off[1] = t01 >> 16; off[2] = t23 & 0xffffu; off[3] = t23 >> 16;
-            }
+            const u32 off[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
 #pragma unroll
             for (int B = 0; B < 4; ++B)
                 if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, off[B]);
@@ -297,11 +320,13 @@ __device__ __forceinline__ void p2_group(const uint4 (&w)[K + 1], const u32 (&ra
     }
 }
 
-template <int K, int THREADS, bool FMAX>
+// [b0, b1): the CTA's slice in 512-row blocks (128 bytes of a packed column)
+template <int K, int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                              long long N, long long g0, long long g1, u32 *hist) {
+                                              long long N, long long b0, long long b1, u32 *hist) {
     constexpr int C = K + 1;
     constexpr int C1 = C > 4 ? C - 4 : 0;
+    constexpr int ROWS = 16 * VEC;            // rows of one thread-iteration
     const uint8_t *cp[C];
     u32 rad[C];
 #pragma unroll
@@ -314,14 +339,29 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
     u32 plow = 1;
 #pragma unroll
     for (int a = C1; a < C; ++a) plow *= rad[a];
-    const u32 mul = m.mul, plow_mul = plow * mul, k16 = m.k16;
+    const u32 mul = m.mul, plow_mul = plow * mul;
+    const long long g0 = b0 * (512 / ROWS), g1 = min(b1 * (512 / ROWS), (N + ROWS - 1) / ROWS);
     for (long long g = g0 + threadIdx.x; g < g1; g += THREADS) {
-        uint4 w[C];
+        u32 w[C][VEC];
 #pragma unroll
-        for (int a = 0; a < C; ++a) w[a] = ld_stream_v4(cp[a] + g * 16);
-        const long long row0 = g * 64;
-        if (row0 + 64 <= N) p2_group<K, false, FMAX>(w, rad, mul, plow_mul, hist, 64, k16);
-        else p2_group<K, true, FMAX>(w, rad, mul, plow_mul, hist, (int)(N - row0), k16);
+        for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
+        const long long row0 = g * ROWS;
+        if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS);
+        else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
+    }
+}
+
+template <int THREADS, int VEC>
+__device__ __forceinline__ void count_rows_p2_k(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
+                                                long long N, long long b0, long long b1, u32 *hist) {
+    switch (m.k) {
+        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
     }
 }
 
@@ -391,8 +431,18 @@ constexpr u32 STAGE_WORDS = 6144;   // staging buffer of the kernels that reduce
 // block with coalesced, independent loads: one CTA walking a 200 k-cell table with dependent
 // 4-byte loads (the first version) spent ~150 us in L2 latency per family.  The order in which a
 // lane meets its configurations is the same either way.
+// Source of an HBM table: one table, or (row-sharded runs with the fused reduce-scatter) the sum of
+// `nsrc` partial tables `sstride` cells apart — the slots the ranks pushed into this rank's exchange
+// buffer; `wb` (nullable) receives the summed table (donors of derived families need it in the arena).
+struct TabSrc {
+    int nsrc;
+    size_t sstride;
+    u32 *wb;
+};
+
 template <bool FROM_GLOBAL, class RowFn>
-__device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap, RowFn row) {
+__device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap, RowFn row,
+                                              TabSrc ts = TabSrc{1, 0, nullptr}) {
     double acc[2] = {0.0, 0.0};
     if (!FROM_GLOBAL) {
 #pragma unroll
@@ -408,14 +458,32 @@ __device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, doub
             const u32 *src = tab + (size_t)base * r;
             __syncthreads();          // the previous piece has been consumed
             u32 i = threadIdx.x;
-            for (; i + 7 * blockDim.x < ncell; i += 8 * blockDim.x) {
-                u32 v[8];
+            if (ts.nsrc == 1 && !ts.wb) {
+                for (; i + 7 * blockDim.x < ncell; i += 8 * blockDim.x) {
+                    u32 v[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __ldcg(src + i + e * blockDim.x);
+                    for (int e = 0; e < 8; ++e) v[e] = __ldcg(src + i + e * blockDim.x);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) stage[i + e * blockDim.x] = v[e];
+                    for (int e = 0; e < 8; ++e) stage[i + e * blockDim.x] = v[e];
+                }
+                for (; i < ncell; i += blockDim.x) stage[i] = __ldcg(src + i);
+            } else {
+                // the partial tables of all ranks: nsrc independent loads per cell, two cells in flight
+                for (; i < ncell; i += 2 * blockDim.x) {
+                    const u32 i2 = i + blockDim.x;
+                    u32 v0 = 0, v1 = 0;
+                    for (int s2 = 0; s2 < ts.nsrc; ++s2) {
+                        v0 += __ldcg(src + (size_t)s2 * ts.sstride + i);
+                        if (i2 < ncell) v1 += __ldcg(src + (size_t)s2 * ts.sstride + i2);
+                    }
+                    stage[i] = v0;
+                    if (i2 < ncell) stage[i2] = v1;
+                    if (ts.wb) {
+                        ts.wb[(size_t)base * r + i] = v0;
+                        if (i2 < ncell) ts.wb[(size_t)base * r + i2] = v1;
+                    }
+                }
             }
-            for (; i < ncell; i += blockDim.x) stage[i] = __ldcg(src + i);
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -445,7 +513,8 @@ __device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, doub
 
 // sum_{j,x: c>0} c * ln(c / N_ij)
 template <bool FROM_GLOBAL>
-__device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap) {
+__device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap,
+                                                TabSrc ts = TabSrc{1, 0, nullptr}) {
     return reduce_rows<FROM_GLOBAL>(tab, q, r, sh, stage, cap, [r](const u32 *row, double &acc) {
         u32 nij = 0;
         for (int x = 0; x < r; ++x) nij += row[x];
@@ -456,14 +525,14 @@ __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, do
                 if (c) acc += (double)c * log((double)c / dn);
             }
         }
-    });
+    }, ts);
 }
 
 // Bayesian-Dirichlet family term (bnlearn "bde" = BDeu, "k2") on the same counts, same lane order:
 // sum_j [ lgamma(a_ij) - lgamma(a_ij + N_ij) + sum_x ( lgamma(a_ijk + c) - lgamma(a_ijk) ) ].
 template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double a_ij, double a_ijk, double *sh,
-                                            u32 *stage, u32 cap) {
+                                            u32 *stage, u32 cap, TabSrc ts = TabSrc{1, 0, nullptr}) {
     const double lg_ij = lgamma(a_ij), lg_ijk = lgamma(a_ijk);
     return reduce_rows<FROM_GLOBAL>(tab, q, r, sh, stage, cap, [=](const u32 *row, double &acc) {
         u32 nij = 0;
@@ -474,17 +543,35 @@ __device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double
             if (c) s += lgamma(a_ijk + (double)c) - lg_ijk;
         }
         if (nij) acc += (lg_ij - lgamma(a_ij + (double)nij)) + s;
-    });
+    }, ts);
 }
 
 // The cached family term: log-likelihood (penalty applied at gather time) or a BD score.
 // FROM_GLOBAL: `stage` / `cap` = shared-memory staging buffer (see reduce_rows).
 template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab, const FamMeta &m, double *sh,
-                                              u32 *stage = nullptr, u32 cap = 0) {
-    if (a.bd_mode == 0) return family_loglik<FROM_GLOBAL>(tab, m.q, m.r, sh, stage, cap);
+                                              u32 *stage = nullptr, u32 cap = 0, TabSrc ts = TabSrc{1, 0, nullptr}) {
+    if (a.bd_mode == 0) return family_loglik<FROM_GLOBAL>(tab, m.q, m.r, sh, stage, cap, ts);
     double a_ijk = a.bd_mode == 1 ? a.iss / ((double)m.q * (double)m.r) : 1.0;
-    return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh, stage, cap);
+    return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh, stage, cap, ts);
+}
+
+// A CTA's slice of the rows in 512-row blocks: 512 bytes of a uint8 column, 128 bytes of a 2-bit
+// packed one, so every warp load covers whole cache lines (ncu showed 5.2 data-pipe wavefronts per
+// 512-byte load with unaligned slices instead of 4).
+__device__ __forceinline__ void slice_blocks(long long N, int slice, int S, long long &b0, long long &b1) {
+    const long long nb = (N + 511) >> 9;
+    b0 = nb * slice / S;
+    b1 = (slice + 1 == S) ? nb : nb * (slice + 1) / S;
+}
+
+// Fused reduce-scatter step of a row-sharded run: the CTA that holds the family's complete LOCAL
+// table (shared memory when the family has one slice, else the merged HBM table) stores it into
+// slot `rank` of the owner rank's exchange buffer with coalesced peer stores over NVLink.
+template <int THREADS, bool FROM_SHARED>
+__device__ __forceinline__ void push_table(const CountArgs &a, int j, const u32 *src, u32 cells) {
+    u32 *dst = a.peer[a.owner[j]] + (size_t)a.rank * a.xcap + a.xoff[j];
+    for (u32 c = threadIdx.x; c < cells; c += THREADS) dst[c] = FROM_SHARED ? src[c] : __ldcg(src + c);
 }
 
 // RANGE (class 3 when the rows dwarf the table): the table does not fit one CTA's shared memory,
@@ -492,9 +579,10 @@ __device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab
 // shared memory, streams the slice and skips the rows whose cell lies elsewhere.  The passes of a
 // slice are neighbours in the grid, so all but the first read the rows from L2.  That trades
 // P x the streaming for shared-memory atomics instead of one L2 atomic per row (measured
-// 0.09-0.19 T/s for the whole GPU).
+// 0.09-0.19 T/s for the whole GPU).  Superseded by k_count_cluster (one pass, table spread over a
+// thread-block cluster) where that is faster; kept for tables beyond a cluster's reach.
 template <int THREADS, bool GLOBAL, bool RANGE = false>
-__global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
+__global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) k_count(CountArgs a) {   // 64 registers: 1024 threads per SM
     static_assert(!(GLOBAL && RANGE), "a sub-range table lives in shared memory");
     extern __shared__ u32 s_hist[];
     __shared__ FamMeta m;
@@ -515,15 +603,10 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     const u32 lo = RANGE ? (u32)pass * a.span : 0u;
     if (RANGE && lo >= cells) return;   // this family needs fewer passes than the largest of the launch
     const u32 span = RANGE ? min(a.span, cells - lo) : cells;
-    // slice boundaries on multiples of 8 vectors (128 bytes): a warp's 512-byte load then covers
-    // exactly 4 cache lines (ncu showed 5.2 data-pipe wavefronts per load with unaligned slices)
+    long long b0, b1;
+    slice_blocks(a.N, slice, a.S, b0, b1);
     const long long nvec = (a.N + 15) >> 4;
-    const long long v0 = (nvec * slice / a.S) & ~7ll;
-    const long long v1 = (slice + 1 == a.S) ? nvec : ((nvec * (slice + 1) / a.S) & ~7ll);
-    // the same slice in 64-row groups of the 2-bit packed copy
-    const long long ngrp = (a.N + 63) >> 6;
-    const long long g0 = (ngrp * slice / a.S) & ~7ll;
-    const long long g1 = (slice + 1 == a.S) ? ngrp : ((ngrp * (slice + 1) / a.S) & ~7ll);
+    const long long v0 = b0 * 32, v1 = min(b1 * 32, nvec);   // 16-row vectors of the uint8 columns
     if (threadIdx.x == 0) {
         // replicas pay off only when the row loop dwarfs zeroing + summing R tables:
         // at least 16 rows per replicated counter
@@ -540,7 +623,6 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         m.R = R;
         m.mul = 4u * R;
         m.lo4 = lo * 4u;
-        m.k16 = 65536u;
         m.span4 = span * 4u;
     }
     __syncthreads();
@@ -553,31 +635,12 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     }
 
     // packed path: all columns <= 4 states, index * mul fits 16-bit lanes.  The choice must not
-    // depend on the slice (the two paths cut the rows into slices differently), hence no R here:
-    // R > 1 implies cells * R <= 16383 (replica selection above).
+    // depend on the slice, hence no R here: R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
-        if (a.fma_extract) {
-            switch (m.k) {
-            case 0: count_rows_p2<0, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 1: count_rows_p2<1, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 2: count_rows_p2<2, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 3: count_rows_p2<3, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 4: count_rows_p2<4, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 5: count_rows_p2<5, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-                default: count_rows_p2<6, THREADS, true>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            }
-        } else {
-            switch (m.k) {
-            case 0: count_rows_p2<0, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 1: count_rows_p2<1, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 2: count_rows_p2<2, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 3: count_rows_p2<3, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 4: count_rows_p2<4, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            case 5: count_rows_p2<5, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-                default: count_rows_p2<6, THREADS, false>(m, a.data2, a.stride2, a.N, g0, g1, hist); break;
-            }
-        }
+        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist);
     } else
     switch (m.k) {
         case 0: count_rows_mode<0, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
@@ -592,16 +655,21 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
     __syncthreads();
     if (!GLOBAL && !RANGE && R > 1) compact_replicas<THREADS>(s_hist, cells, R);
 
+    const bool single = !GLOBAL && !RANGE && a.S == 1;   // the CTA's shared-memory table is the whole local table
+    if (a.push && single) {   // row-sharded: straight from shared memory to the owner rank, no local HBM copy
+        push_table<THREADS, true>(a, j, s_hist, cells);
+        return;
+    }
     if (!GLOBAL && tab) {   // merge this slice's shared-memory table into the HBM table
         for (u32 c = threadIdx.x; c < span; c += THREADS) {
             u32 v = s_hist[c];
             if (v) atomicAdd(tab + lo + c, v);
         }
     }
-    if (!a.reduce) return;
+    if (!a.reduce && !a.push) return;
 
     double ll;
-    if (!GLOBAL && !RANGE && a.S == 1) {
+    if (single) {
         ll = family_term<false>(a, s_hist, m, s_red);
     } else {
         const u32 parts = RANGE ? (u32)a.S * ((cells + a.span - 1) / a.span) : (u32)a.S;
@@ -611,15 +679,154 @@ __global__ void __launch_bounds__(THREADS) k_count(CountArgs a) {
         __syncthreads();
         if (!s_last) return;
         __threadfence();
+        if (a.push) {   // the local table is complete: hand it to the owner rank
+            push_table<THREADS, false>(a, j, tab, cells);
+            return;
+        }
         ll = family_term<true>(a, tab, m, s_red, s_hist, a.stage_words);
     }
     if (threadIdx.x == 0) {
-        a.ll_out[a.key_base + j] = ll;
-        a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
+        a.ll_out[a.out_base + j] = ll;
+        a.np_out[a.out_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
     }
 }
 
-// k3 alone: reduce HBM tables after the cross-GPU all-reduce (row-sharded datasets).
+// ---------------------------------------------------------------------------------------
+// Class 3 in ONE pass over the rows: a thread-block cluster of CL CTAs (2, 4 or 8; one CTA per SM)
+// holds the table of a (family, slice) in distributed shared memory, cell c in CTA c % CL at word
+// c / CL (interleaved, so that skewed distributions load the CTAs evenly).  Every CTA streams 1/CL
+// of the slice, computes each row's cell once and increments the owning CTA's counter with
+// red.shared::cluster over the SM-to-SM network.  The sub-range passes above recompute the index
+// of every row in each of P passes and discard (P - 1) / P of them (ncu: issue-active 76 %, ALU
+// 66 %, 0.15 of the HBM peak).
+__device__ __forceinline__ u32 cluster_ctarank() {
+    u32 r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one increment of the counter at shared-memory byte address `local` of CTA `rank` of this cluster
+__device__ __forceinline__ void cluster_inc(u32 local, u32 rank) {
+    u32 remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(remote), "r"(1u) : "memory");
+}
+
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_cluster(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                                   long long N, long long v0, long long v1, u32 hist_addr, u32 clmask,
+                                                   u32 clshift) {
+    const uint8_t *cp[K + 1];
+    u32 rad[K + 1];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
+        uint4 w[K + 1];
+#pragma unroll
+        for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
+        u32 cell[16];
+        cells_u32<K>(w, rad, 1u, cell);
+        const int nv = v * 16 + 16 <= N ? 16 : (int)(N - v * 16);
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+            if (b < nv) cluster_inc(hist_addr + ((cell[b] >> clshift) << 2), cell[b] & clmask);
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_count_cluster(CountArgs a, int CL) {
+    extern __shared__ u32 s_hist[];
+    __shared__ FamMeta m;
+    __shared__ double s_red[32];
+    __shared__ int s_last;
+    const u32 rank = cluster_ctarank();
+    const int item = blockIdx.x / CL;            // (slice, family), slice-major
+    const int slice = item / a.njobs;
+    const int j = a.jobs[item - slice * a.njobs];
+    if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
+    __syncthreads();
+    const u32 cells = m.cells;
+    const u32 clshift = 31 - __clz(CL), clmask = (u32)CL - 1u;
+    const u32 words = (cells + clmask - rank) >> clshift;   // cells c < cells with c % CL == rank
+    for (u32 c = threadIdx.x; c < words; c += THREADS) s_hist[c] = 0;
+    cluster_sync_all();                                     // every CTA's table is zeroed before the first remote increment
+
+    long long b0, b1;
+    slice_blocks(a.N, slice, a.S, b0, b1);
+    const long long bq0 = b0 + (b1 - b0) * rank / CL, bq1 = b0 + (b1 - b0) * (rank + 1) / CL;   // this CTA's share of the slice
+    const long long nvec = (a.N + 15) >> 4;
+    const long long v0 = bq0 * 32, v1 = min(bq1 * 32, nvec);
+    const u32 hist_addr = (u32)__cvta_generic_to_shared(s_hist);
+    switch (m.k) {
+        case 0: count_rows_cluster<0, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        case 1: count_rows_cluster<1, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        case 2: count_rows_cluster<2, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        case 3: count_rows_cluster<3, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        case 4: count_rows_cluster<4, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        case 5: count_rows_cluster<5, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        case 6: count_rows_cluster<6, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist_addr, clmask, clshift); break;
+        default: {   // k > 6: columns one at a time
+            const uint8_t *child = a.data + (long long)m.node * a.stride;
+            for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
+                u32 cell[16];
+#pragma unroll
+                for (int b = 0; b < 16; ++b) cell[b] = 0;
+                for (int x = 0; x <= m.k; ++x) {
+                    uint4 w = ld_stream_v4((x < m.k ? a.data + (long long)m.par[x] * a.stride : child) + v * 16);
+                    const u32 rad = x < m.k ? m.rad[x] : (u32)m.r;
+                    const u32 ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) cell[i * 4 + b] = cell[i * 4 + b] * rad + ((ws[i] >> (8 * b)) & 0xffu);
+                }
+                const int nv = v * 16 + 16 <= a.N ? 16 : (int)(a.N - v * 16);
+#pragma unroll
+                for (int b = 0; b < 16; ++b)
+                    if (b < nv) cluster_inc(hist_addr + ((cell[b] >> clshift) << 2), cell[b] & clmask);
+            }
+        }
+    }
+    cluster_sync_all();   // all increments of the cluster have landed; nobody touches remote shared memory after this
+
+    // this CTA's interleaved share of the table goes to the HBM table (always: the fp64 reduce needs it in one place)
+    u32 *tab = a.arena + a.table_off[j];
+    for (u32 c = threadIdx.x; c < words; c += THREADS) {
+        const u32 v = s_hist[c];
+        if (v) {
+            if (a.S == 1) tab[(c << clshift) + rank] = v;   // the arena is zeroed; one writer per cell
+            else atomicAdd(tab + (c << clshift) + rank, v);
+        }
+    }
+    if (!a.reduce && !a.push) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.done + j, 1u) == (u32)(a.S * CL) - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (a.push) {
+        push_table<THREADS, false>(a, j, tab, cells);
+        return;
+    }
+    const double ll = family_term<true>(a, tab, m, s_red, s_hist, a.stage_words);
+    if (threadIdx.x == 0) {
+        a.ll_out[a.out_base + j] = ll;
+        a.np_out[a.out_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
+    }
+}
+
+// k3 alone: reduce HBM tables of a row-sharded run.  Without the fused reduce-scatter (world 1, the
+// caller wants every table, or the exchange buffer is too small) every rank holds the all-reduced
+// tables in its arena and reduces all of them.  With it (a.push) a rank reduces only the families it
+// owns, from the `world` partial tables the ranks pushed into its exchange buffer.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njobs) {
     __shared__ FamMeta m;
@@ -628,12 +835,19 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     const int j = blockIdx.x;
     if (j >= njobs) return;
     if (a.donor && a.donor[j] >= 0) return;   // derived families are reduced by k_derive
+    if (a.push && a.owner[j] != a.rank) return;
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
-    double ll = family_term<true>(a, a.arena + a.table_off[j], m, s_red, s_stage, STAGE_WORDS);
+    double ll;
+    if (a.push) {
+        TabSrc ts{a.world, (size_t)a.xcap, a.writeback ? a.arena + a.table_off[j] : nullptr};
+        ll = family_term<true>(a, a.peer[a.rank] + a.xoff[j], m, s_red, s_stage, STAGE_WORDS, ts);
+    } else {
+        ll = family_term<true>(a, a.arena + a.table_off[j], m, s_red, s_stage, STAGE_WORDS);
+    }
     if (threadIdx.x == 0) {
-        a.ll_out[a.key_base + j] = ll;
-        a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
+        a.ll_out[a.out_base + j] = ll;
+        a.np_out[a.out_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
     }
 }
 
@@ -657,6 +871,7 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
     __shared__ u32 s_nx, s_xcells;
     __shared__ int s_last;
     const int j = level_list[blockIdx.x / dch];
+    if (a.push && a.owner[j] != a.rank) return;   // the donor's global table lives on the owner rank only
     const u32 chunk = blockIdx.x % dch;
     const u32 nchunks = min((u32)dch, max(1u, cells_arr[a.donor[j]] / 4096u));
     if (chunk >= nchunks) return;
@@ -735,8 +950,8 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
     __threadfence();
     double ll = family_term<true>(a, mt, m, s_red, s_stage, STAGE_WORDS);
     if (threadIdx.x == 0) {
-        a.ll_out[a.key_base + j] = ll;
-        a.np_out[a.key_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
+        a.ll_out[a.out_base + j] = ll;
+        a.np_out[a.out_base + j] = a.bd_mode ? 0.0 : (double)(m.r - 1) * (double)m.q;
     }
 }
 

@@ -22,6 +22,12 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
+def _current_stream(t) -> int:
+    """The CUDA stream torch would launch on for tensor ``t``'s device (the producer of ``t``)."""
+    import torch
+    return int(torch.cuda.current_stream(t.device).cuda_stream)
+
+
 def _family_csr(nodes: Sequence[int], parent_lists: Sequence[Iterable[int]]):
     node = np.ascontiguousarray(nodes, dtype=np.int32)
     lens = np.fromiter((len(p) for p in parent_lists), dtype=np.int64, count=len(parent_lists))
@@ -48,6 +54,8 @@ class BicScorer:
             msg = self._lib.bic_last_error(None)
             self._ctx = ctypes.c_void_p()
             raise nat.BicError(rc, msg.decode() if msg else "")
+        self._iss = 1.0
+        self._shard = (0, 1)     # (rank, world) when the rows are sharded
         self.set_dataset(codes, card)
         if iss != 1.0:
             self.set_iss(iss)
@@ -55,6 +63,7 @@ class BicScorer:
     def set_iss(self, iss: float) -> None:
         """Imaginary sample size of the ``bde`` (BDeu) metric, bnlearn's ``iss`` (default 1)."""
         self._check(self._lib.bic_set_iss(self._ctx, float(iss)))
+        self._iss = float(iss)
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
@@ -77,6 +86,13 @@ class BicScorer:
     def _check(self, rc: int) -> None:
         nat.check(self._ctx, rc)
 
+    def _after_producer(self, tensor) -> None:
+        """Device inputs: whatever torch queued on its current stream (the decoder, a dtype
+        conversion, an all-gather) must finish before the library's kernels read the buffer.  The
+        library runs on its own stream, so the ordering is made explicit: an event on torch's
+        stream that the context's stream waits on (``bic_wait_stream``; no host synchronisation)."""
+        self._check(self._lib.bic_wait_stream(self._ctx, ctypes.c_void_p(_current_stream(tensor))))
+
     # ------------------------------------------------------------------- dataset
     def set_dataset(self, codes, card) -> None:
         """codes: uint8 ``[n, N]`` (variable-major, i.e. column-major samples); card: ``[n]``."""
@@ -90,6 +106,7 @@ class BicScorer:
             codes = codes.contiguous()
             n, N = int(codes.shape[0]), int(codes.shape[1])
             ptr, is_dev, stride = codes.data_ptr(), 1, N
+            self._after_producer(codes)
         else:
             codes = np.ascontiguousarray(codes, dtype=np.uint8)
             if codes.ndim != 2:
@@ -171,6 +188,7 @@ class BicScorer:
             import torch
             a = adj.reshape(-1, n, n).to(torch.uint8).contiguous()
             out = torch.empty(a.shape[0], dtype=torch.float64, device=a.device)
+            self._after_producer(a)
             self._check(self._lib.bic_score_dags_adj(self._ctx, a.data_ptr(), a.shape[0], self._metric(metric),
                                                      out.data_ptr(), ctypes.byref(inv),
                                                      self._flags(check_acyclic, no_cache, True)))
@@ -185,11 +203,13 @@ class BicScorer:
         return (out, int(inv.value)) if return_invalid else out
 
     def score_adjacency_into(self, adj_ptr: int, B: int, out_ptr: int, device: bool, metric: Optional[str] = None,
-                             check_acyclic: bool = True, no_cache: bool = False) -> int:
-        """Raw-pointer variant (what bench.py times): no allocation, no conversion."""
+                             check_acyclic: bool = True, no_cache: bool = False, extra_flags: int = 0) -> int:
+        """Raw-pointer variant (what bench.py times): no allocation, no conversion, no stream ordering —
+        device inputs must be complete (see ``bic_wait_stream``).  ``extra_flags``: e.g.
+        ``FLAG_LOCAL_BATCH`` for a family-sharded scorer."""
         inv = ctypes.c_int64(0)
-        self._check(self._lib.bic_score_dags_adj(self._ctx, adj_ptr, B, self._metric(metric), out_ptr,
-                                                 ctypes.byref(inv), self._flags(check_acyclic, no_cache, device)))
+        self._check(self._lib.bic_score_dags_adj(self._ctx, adj_ptr, B, self._metric(metric), out_ptr, ctypes.byref(inv),
+                                                 self._flags(check_acyclic, no_cache, device) | int(extra_flags)))
         return int(inv.value)
 
     def score_csr_into(self, off_ptr: int, parents_ptr: int, B: int, out_ptr: int, device: bool,
@@ -219,26 +239,56 @@ class BicScorer:
     def score_wire(self, labels, ebits, metric: Optional[str] = None, no_cache: bool = False,
                    return_invalid: bool = False):
         """Reference candidate wire format (``src/toolkit/labeled.py:116-154``): ``labels[b, v]`` =
-        BN variable of vertex v, bit u of ``ebits[b, v]`` <=> edge vertex u -> vertex v."""
+        BN variable of vertex v (uint16, any n), ``ebits[b, v, w]`` = 32-bit edge words, bit ``u % 32``
+        of word ``u // 32`` <=> edge vertex u -> vertex v (``[B, n]`` is accepted for n <= 32).
+        CUDA tensors in -> CUDA tensor out (decoder output that never leaves the GPU)."""
         inv = ctypes.c_int64(0)
-        if _is_torch(labels) and labels.is_cuda:     # decoder output that never leaves the GPU
+        n = self.n
+        ew_min = (n + 31) // 32
+        if _is_torch(labels) and labels.is_cuda:
             import torch
-            lab = labels.reshape(-1, self.n).to(torch.uint8).contiguous()
-            eb = ebits.reshape(-1, self.n).to(torch.int32).contiguous()     # bit pattern of the uint32 words
-            out = torch.empty(lab.shape[0], dtype=torch.float64, device=lab.device)
-            self._check(self._lib.bic_score_dags_wire(self._ctx, lab.data_ptr(), eb.data_ptr(), lab.shape[0],
-                                                      self._metric(metric), out.data_ptr(), ctypes.byref(inv),
-                                                      self._flags(True, no_cache, True)))
+            lab = labels.reshape(-1, n).to(torch.int64)
+            B = lab.shape[0]
+            # a label outside 0..65535 must not wrap into the valid range: 65535 is rejected by the kernel (n <= 1024)
+            lab = torch.where((lab < 0) | (lab > 65535), torch.full_like(lab, 65535), lab)
+            lab16 = lab.to(torch.uint16).contiguous()
+            eb = ebits.reshape(B, n, -1).to(torch.int32).contiguous()       # bit pattern of the uint32 words
+            if eb.shape[2] < ew_min:
+                raise ValueError(f"ebits needs {ew_min} words per vertex for n = {n}")
+            out = torch.empty(B, dtype=torch.float64, device=lab16.device)
+            self._after_producer(eb)
+            self._check(self._lib.bic_score_dags_wire16(self._ctx, lab16.data_ptr(), eb.data_ptr(), eb.shape[2], B,
+                                                        self._metric(metric), out.data_ptr(), ctypes.byref(inv),
+                                                        self._flags(True, no_cache, True)))
             return (out, int(inv.value)) if return_invalid else out
-        labels = np.ascontiguousarray(labels, dtype=np.uint8).reshape(-1, self.n)
-        ebits = np.ascontiguousarray(ebits, dtype=np.uint32).reshape(-1, self.n)
-        if labels.shape != ebits.shape:
-            raise ValueError("labels and ebits must both be [B, n]")
+        labels = np.asarray(labels)
+        if labels.size and (labels.min() < 0 or labels.max() > 65535):
+            labels = np.where((labels < 0) | (labels > 65535), 65535, labels)
+        labels = np.ascontiguousarray(labels, dtype=np.uint16).reshape(-1, n)
+        ebits = np.ascontiguousarray(ebits, dtype=np.uint32).reshape(labels.shape[0], n, -1)
+        if ebits.shape[2] < ew_min:
+            raise ValueError(f"ebits needs {ew_min} words per vertex for n = {n}")
         out = np.empty(labels.shape[0], dtype=np.float64)
-        self._check(self._lib.bic_score_dags_wire(self._ctx, labels.ctypes.data, ebits.ctypes.data, labels.shape[0],
-                                                  self._metric(metric), out.ctypes.data, ctypes.byref(inv),
-                                                  self._flags(True, no_cache, False)))
+        self._check(self._lib.bic_score_dags_wire16(self._ctx, labels.ctypes.data, ebits.ctypes.data, ebits.shape[2],
+                                                    labels.shape[0], self._metric(metric), out.ctypes.data,
+                                                    ctypes.byref(inv), self._flags(True, no_cache, False)))
         return (out, int(inv.value)) if return_invalid else out
+
+    def score_adjacency_local(self, adj, metric: Optional[str] = None, check_acyclic: bool = True):
+        """Family-sharded scoring of a sharded candidate batch: ``adj`` holds THIS rank's B DAGs (CUDA
+        tensor ``[B, n, n]``, same B on every rank).  The family keys are all-gathered over NVLink
+        inside the library, the union is deduplicated identically on every rank, each rank counts only
+        the families it owns and returns the scores of its own B DAGs."""
+        import torch
+        n = self.n
+        a = adj.reshape(-1, n, n).to(torch.uint8).contiguous()
+        out = torch.empty(a.shape[0], dtype=torch.float64, device=a.device)
+        inv = ctypes.c_int64(0)
+        self._after_producer(a)
+        self._check(self._lib.bic_score_dags_adj(self._ctx, a.data_ptr(), a.shape[0], self._metric(metric), out.data_ptr(),
+                                                 ctypes.byref(inv),
+                                                 self._flags(check_acyclic, False, True) | nat.FLAG_LOCAL_BATCH))
+        return out
 
     # --------------------------------------------------------------------- cache
     def cache_clear(self) -> None:
@@ -254,7 +304,6 @@ class BicScorer:
 
     def save_cache(self, path: str) -> int:
         """Checkpoint the family-score cache (keys + terms) to an ``.npz``; returns the family count."""
-        import hashlib
         fam, kind = ctypes.c_int64(0), ctypes.c_int32(0)
         self._check(self._lib.bic_cache_export(self._ctx, None, None, None, 0, ctypes.byref(fam), ctypes.byref(kind)))
         F, Wk = int(fam.value), 1 + (self.n + 63) // 64
@@ -264,19 +313,30 @@ class BicScorer:
         if F:
             self._check(self._lib.bic_cache_export(self._ctx, keys.ctypes.data, terms.ctypes.data, nparams.ctypes.data, F,
                                                    ctypes.byref(fam), ctypes.byref(kind)))
-        tag = hashlib.sha256(np.asarray([self.n, self.N], dtype=np.int64).tobytes() + self.card.tobytes()).hexdigest()
         np.savez_compressed(path, keys=keys[:F], terms=terms[:F], nparams=nparams[:F], kind=np.int32(kind.value),
-                            dataset_tag=np.array(tag), n=np.int64(self.n), N=np.int64(self.N))
+                            dataset_tag=np.array(self._dataset_tag(int(kind.value))), n=np.int64(self.n), N=np.int64(self.N))
         return F
+
+    def _dataset_tag(self, kind: int) -> str:
+        """What a cache checkpoint is valid for: the dataset's content (device-side fingerprint of every
+        code), its shape and cardinalities, the sharding of the rows, and ``iss`` for bde terms."""
+        import hashlib
+        fp = ctypes.c_uint64(0)
+        self._check(self._lib.bic_dataset_fingerprint(self._ctx, ctypes.byref(fp)))
+        h = hashlib.sha256(np.asarray([self.n, self.N, self._shard[0], self._shard[1]], dtype=np.int64).tobytes())
+        h.update(np.asarray([fp.value], dtype=np.uint64).tobytes())
+        h.update(self.card.tobytes())
+        if kind == 1:
+            h.update(np.asarray([self._iss], dtype=np.float64).tobytes())
+        return h.hexdigest()
 
     def load_cache(self, path: str) -> int:
         """Resume from ``save_cache``: replaces the cache content.  Refuses a checkpoint made with
         another dataset shape / cardinalities."""
-        import hashlib
         d = np.load(path)
-        tag = hashlib.sha256(np.asarray([self.n, self.N], dtype=np.int64).tobytes() + self.card.tobytes()).hexdigest()
-        if str(d["dataset_tag"]) != tag:
-            raise ValueError("cache checkpoint was made with a different dataset (n, N or cardinalities differ)")
+        if str(d["dataset_tag"]) != self._dataset_tag(int(d["kind"])):
+            raise ValueError("cache checkpoint was made with a different dataset (content, shape, cardinalities, "
+                             "row sharding or iss differ)")
         keys = np.ascontiguousarray(d["keys"], dtype=np.uint64)
         terms = np.ascontiguousarray(d["terms"], dtype=np.float64)
         nparams = np.ascontiguousarray(d["nparams"], dtype=np.float64)
@@ -312,12 +372,15 @@ class BicScorer:
         with an NCCL uint32 all-reduce before the fp64 reduce.  See ``dist.py``."""
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self._lib.bic_comm_init(self._ctx, ctypes.addressof(buf), int(rank), int(world)))
+        self._shard = (int(rank), int(world))
 
     def init_family_sharding(self, rank: int, world: int, unique_id: bytes) -> None:
         """Dataset replicated, every rank is given the same global candidate batch; each rank counts
         only the families it owns and the terms are all-reduced (bit-identical to one GPU)."""
         self.init_row_sharding(rank, world, unique_id)
         self._check(self._lib.bic_comm_mode(self._ctx, 1))
+        self._shard = (0, 1)     # every rank holds all rows
 
     def end_row_sharding(self) -> None:
         self._check(self._lib.bic_comm_destroy(self._ctx))
+        self._shard = (0, 1)

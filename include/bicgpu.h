@@ -25,6 +25,15 @@
  * every array argument of that call (inputs and outputs) is a device pointer on the context's
  * GPU.  Pointers are borrowed for the duration of the call.  Calls on one context are
  * serialised; use one context per GPU (one process per GPU for multi-GPU runs).
+ *
+ * Stream ordering of device pointers.  The library launches on the context's own non-blocking
+ * stream (or the one given to bic_set_stream) and every scoring call returns only after that
+ * stream has drained, so OUTPUTS are complete on return.  INPUTS are the caller's business: work
+ * that produces a device input on another stream (a decoder, a dtype conversion, an all-gather)
+ * is NOT ordered before the library's kernels unless the caller either synchronises that stream,
+ * hands it over with bic_set_stream, or calls bic_wait_stream(ctx, producer_stream) right before
+ * the scoring call (an event on the producer stream that the context's stream waits on; no host
+ * synchronisation).  The Python host layer does the latter for every CUDA tensor it is given.
  */
 #ifndef BICGPU_H
 #define BICGPU_H
@@ -35,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BICGPU_VERSION 100
+#define BICGPU_VERSION 200
 
 typedef struct bic_ctx bic_ctx;
 
@@ -60,8 +69,12 @@ enum {
     BIC_FLAG_DEVICE_PTRS = 1,    /* array arguments are device pointers                       */
     BIC_FLAG_NO_CYCLE_CHECK = 2, /* skip the acyclicity check (bnlearn_score.R:35 does check) */
     BIC_FLAG_NO_CACHE = 4,       /* clear the family-score cache before this call             */
-    BIC_FLAG_NO_DERIVE = 8       /* count every new family from the rows, even when its table  *
+    BIC_FLAG_NO_DERIVE = 8,      /* count every new family from the rows, even when its table  *
                                   * could be marginalised from a counted superset family       */
+    BIC_FLAG_LOCAL_BATCH = 16    /* bic_score_dags_*, family sharding only: the arrays hold THIS *
+                                  * rank's B DAGs (same B on every rank); the library all-gathers *
+                                  * the family keys over NVLink, deduplicates the union on every  *
+                                  * rank and returns the B local scores                           */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -75,6 +88,10 @@ const char *bic_last_error(const bic_ctx *ctx);
  * context's own stream.  NULL restores the own stream. */
 int bic_set_stream(bic_ctx *ctx, void *cuda_stream);
 int bic_sync(bic_ctx *ctx);
+/* Order everything queued so far on `producer_stream` (a cudaStream_t; NULL = the legacy default
+ * stream) before the kernels of the following calls on this context.  No host synchronisation.
+ * See "Stream ordering of device pointers" above. */
+int bic_wait_stream(bic_ctx *ctx, void *producer_stream);
 /* Imaginary sample size of the "bde" metric (bnlearn's iss argument; default 1).  Clears cached
  * bde terms. */
 int bic_set_iss(bic_ctx *ctx, double iss);
@@ -86,6 +103,10 @@ int bic_set_iss(bic_ctx *ctx, double iss);
  * Clears the family-score cache. */
 int bic_set_dataset(bic_ctx *ctx, const uint8_t *codes, int64_t N, int32_t n, int64_t stride,
                     const int32_t *card, int is_device);
+/* 64-bit content fingerprint of the dataset held by the context (computed on the device; depends
+ * on every code, N and n).  Cache checkpoints carry it so that a checkpoint made on other rows of
+ * the same shape (a bootstrap resample, another row shard) is refused. */
+int bic_dataset_fingerprint(bic_ctx *ctx, uint64_t *out);
 
 /* ---- families --------------------------------------------------------------------------
  * Replaces: the per-node contingency counting inside bnlearn::score (call site
@@ -118,6 +139,13 @@ int bic_score_dags_csr(bic_ctx *ctx, const int64_t *off, const int32_t *parents,
  * (bnlearn.py:34-35 asserts). */
 int bic_score_dags_wire(bic_ctx *ctx, const uint8_t *labels, const uint32_t *ebits, int64_t B,
                         int metric, double *out, int64_t *n_invalid, int flags);
+/* The wire format for any n <= 1024, with the reference's own label type (l_i is uint16,
+ * src/toolkit/labeled.py:118; e_i has i characters, :124): labels [B][n] uint16, ebits
+ * [B][n][ewords] with ewords >= ceil(n / 32), bit (u % 32) of word (u / 32) of ebits[b][v] set
+ * <=> edge vertex u -> vertex v (u < v; bits at u >= v are ignored).  A label >= n or a repeated
+ * label rejects the DAG (bnlearn.py:34-35). */
+int bic_score_dags_wire16(bic_ctx *ctx, const uint16_t *labels, const uint32_t *ebits, int32_t ewords,
+                          int64_t B, int metric, double *out, int64_t *n_invalid, int flags);
 
 /* ---- family-score cache ---------------------------------------------------------------- */
 typedef struct {
@@ -159,6 +187,11 @@ typedef struct {
     int64_t class_families[4];
     int64_t class_alg_bytes[4];
     int64_t families_derived; /* new families whose table was marginalised from a superset's  */
+    /* row-sharded runs: the exchange step after the count kernels (barrier or ncclAllReduce of the
+     * tables + the fp64 reduce from HBM), CUDA-event time; bytes this rank sent: count tables stored
+     * into peers' exchange buffers (fused reduce-scatter) or the all-reduced payload (NCCL path) */
+    double exchange_ms;
+    int64_t exchange_bytes;
 } bic_profile_t;
 int bic_profile_enable(bic_ctx *ctx, int on);
 int bic_profile_reset(bic_ctx *ctx);
@@ -185,14 +218,23 @@ typedef struct {
     int32_t slices[4];         /* row slices per family, per class                              */
     int32_t ranged;            /* 1: class 3 in shared-memory sub-range passes                  */
     int32_t passes;            /* sub-range passes per (family, slice) when ranged, else 1      */
+    int32_t cluster;           /* > 0: class 3 in one pass over thread-block clusters of this   *
+                                * many CTAs that share the table in distributed shared memory   */
 } bic_plan_out_t;
 int bic_plan_slices(const bic_plan_in_t *in, bic_plan_out_t *out);
 
 /* ---- row sharding over several GPUs (one process per GPU) ------------------------------
  * Each rank holds N_rank rows of the same n columns.  After bic_comm_init every scoring call
- * must be made collectively with identical family / DAG arguments on every rank: partial
- * count tables are summed with ncclAllReduce(uint32) over NVLink before the fp64 reduce, and
- * ln N uses the global row count.  NCCL is dlopen()ed ("libnccl.so.2") on first use.
+ * must be made collectively with identical family / DAG arguments on every rank.  The partial
+ * count tables are summed by a reduce-scatter fused into the count kernels: every family has an
+ * owner rank, the CTA that completes a family's local table stores it into the owner's exchange
+ * buffer with peer stores over NVLink (buffers mapped with CUDA IPC at the first call), a 4-byte
+ * all-reduce orders the stores, the owner sums the partial tables inside its fp64 reduce and the
+ * family terms travel with one ncclAllReduce(double).  Where peer mapping is unavailable, the
+ * caller wants the tables themselves (bic_count_families) or a batch exceeds the exchange buffer,
+ * the tables are summed with ncclAllReduce(uint32) instead.  Either way the counts are integer
+ * sums (bit-exact for any number of ranks), every rank ends with identical bits and ln N uses
+ * the global row count.  NCCL is dlopen()ed ("libnccl.so.2") on first use.
  * bic_comm_unique_id: rank 0 creates the 128-byte id and ships it to the others (e.g. with
  * torch.distributed.broadcast). */
 int bic_comm_unique_id(uint8_t id_out[128]);

@@ -52,8 +52,39 @@ def main():
     got2 = s.score_adjacency(np.concatenate([dags[:50], dags2]))
     want2 = np.concatenate([want[:50], C.score_dags_adj(codes, card, dags2)])
     assert (np.abs(got2 - want2) / np.abs(want2)).max() < 1e-9
+    prof_rows = s.profile()
     s.end_row_sharding()
     s.close()
+    # the same through ncclAllReduce(uint32) of the tables (BIC_NO_PUSH=1): identical bits
+    os.environ["BIC_NO_PUSH"] = "1"
+    s2 = pkg.BicScorer(np.ascontiguousarray(codes[:, lo:hi]), card, device=local)
+    os.environ.pop("BIC_NO_PUSH")
+    bdist.init_row_sharding(s2)
+    assert np.array_equal(s2.score_adjacency(dags), got)
+    s2.end_row_sharding()
+    s2.close()
+    # class 2 / class 3 tables and derived families through the exchange buffers (rows >= 2^20 per rank)
+    N3 = 2_200_001
+    card3 = np.array([21, 20, 19, 3, 3, 3, 2, 4], dtype=np.int32)
+    rng3 = np.random.default_rng(6)
+    codes3 = np.stack([rng3.integers(0, c, size=N3) for c in card3]).astype(np.uint8)
+    lo3, hi3 = bdist.shard_range(N3, rank, world)
+    s3 = pkg.BicScorer(np.ascontiguousarray(codes3[:, lo3:hi3]), card3, device=local)
+    bdist.init_row_sharding(s3)
+    fams3 = [(3, [0, 1]), (4, [0, 1, 2]), (3, [0, 1, 2, 5]), (6, [7]), (7, [3, 4, 6]), (6, [3, 7]), (5, [])]
+    node3 = np.array([f[0] for f in fams3], dtype=np.int32)
+    off3 = np.zeros(len(fams3) + 1, dtype=np.int64)
+    off3[1:] = np.cumsum([len(f[1]) for f in fams3])
+    par3 = np.array([p for f in fams3 for p in f[1]], dtype=np.int32)
+    s3.profile_reset()
+    got3 = s3.score_families([f[0] for f in fams3], [f[1] for f in fams3])
+    want3 = C.score_families(codes3, card3, node3, off3, par3)
+    assert (np.abs(got3 - want3) / np.abs(want3)).max() < 1e-9
+    assert s3.profile()["families_derived"] > 0
+    for (i, ps), t in zip(fams3[:3], s3.count_families([f[0] for f in fams3[:3]], [f[1] for f in fams3[:3]])):
+        assert np.array_equal(t, C.family_counts(codes3, card3, i, ps)) and t.sum() == N3
+    s3.end_row_sharding()
+    s3.close()
 
     # ---- candidate sharding
     full = pkg.BicScorer(codes, card, device=local)
@@ -83,6 +114,10 @@ def main():
     dist.all_reduce(counted)
     st = fam.cache_stats()
     assert int(counted.sum()) == st["families"] and prof["families_counted"] < st["families"]   # the work was split
+    if (bhi - blo) * world == len(dags):                    # every rank passes only its own DAGs (BIC_FLAG_LOCAL_BATCH)
+        fam.cache_clear()
+        mine_scores = fam.score_adjacency_local(mine_cuda)
+        assert np.array_equal(mine_scores.cpu().numpy(), want_bits[blo:bhi])
     got_f2 = fam.score_adjacency(dags2)                     # second batch: cached + new families
     one = pkg.BicScorer(codes2, card, device=local)
     one.score_adjacency(dags)

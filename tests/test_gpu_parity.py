@@ -436,38 +436,52 @@ def test_packed_and_byte_paths_agree(monkeypatch):
 
 
 # ----------------------------------- tables above one CTA's shared memory (class 3), slicing
-def test_class3_subrange_passes_match_oracle_and_l2_atomics(monkeypatch):
-    """Tables of more than 49152 cells: when the rows dwarf the table it is counted in passes over
-    shared-memory sub-ranges (k_count<512,false,true>), otherwise straight into HBM with L2
-    atomics.  Both must give the oracle's counts and identical score bits; ragged row count,
-    k <= 6 (specialised row loop) and k > 6 (generic loop), one and several row slices."""
+def test_class3_cluster_passes_and_l2_atomics_match_oracle(monkeypatch):
+    """Tables of more than 49152 cells.  When the rows dwarf the table it is counted in ONE pass by a
+    thread-block cluster whose CTAs share the table in distributed shared memory (k_count_cluster,
+    the default), or in passes over shared-memory sub-ranges (k_count<1024,false,true>,
+    BIC_CLUSTER=0); otherwise straight into HBM with L2 atomics.  All three must give the oracle's
+    counts and identical score bits; ragged row count, k <= 6 (specialised row loop) and k > 6
+    (generic loop), one and several row slices, cluster sizes 2 / 4 / 8."""
     N = 1_200_003
     rng = np.random.default_rng(77)
     card = np.array([21, 20, 19, 5, 7] + [3] * 11, dtype=np.int32)
     codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
     codes[3] = (codes[0] + codes[4]) % 5                      # structure: not every cell is hit equally
-    fams = [(4, [0, 1, 2]),                                   # 55 860 cells: 2 passes
-            (0, [1, 2, 3, 4]),                                # 279 300 cells: 6 passes
+    fams = [(4, [0, 1, 2]),                                   # 55 860 cells: 2 CTAs / 2 passes
+            (0, [1, 2, 3, 4]),                                # 279 300 cells: 8 CTAs / 6 passes
             (5, list(range(6, 16))),                          # 3^11 = 177 147 cells, k = 10
             (3, [0, 1, 2])]                                   # 39 900 cells: class 2, same launch sequence
     node, off, par = csr_of(fams)
-    with pkg.BicScorer(codes, card) as s:
-        s.profile_reset()
-        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
-        for (i, ps), t in zip(fams, tabs):
-            assert t.sum() == N
-            assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (i, ps)
-        ranged = s.score_families_csr(node, off, par, no_cache=True)
-        one = s.score_families([4], [[0, 1, 2]], no_cache=True)          # alone: several row slices
-        assert one[0] == ranged[0]
-        assert np.array_equal(s.family_counts(4, [0, 1, 2]), tabs[0])
-    assert_scores(ranged, C.score_families(codes, card, node, off, par))
+    want_tabs = [C.family_counts(codes, card, i, ps) for i, ps in fams]
+    want_scores = C.score_families(codes, card, node, off, par)
+
+    def run():
+        with pkg.BicScorer(codes, card) as s:
+            tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+            for (i, ps), t, w in zip(fams, tabs, want_tabs):
+                assert t.sum() == N
+                assert np.array_equal(t, w), (i, ps)
+            scores = s.score_families_csr(node, off, par, no_cache=True)
+            one = s.score_families([4], [[0, 1, 2]], no_cache=True)          # alone: several row slices, smaller cluster
+            assert one[0] == scores[0]
+            assert np.array_equal(s.family_counts(4, [0, 1, 2]), tabs[0])
+            two = s.score_families([5], [list(range(6, 16))], no_cache=True)     # 4 CTAs per cluster when alone
+            assert two[0] == scores[2]
+        assert_scores(scores, want_scores)
+        return scores
+
+    clustered = run()
+    monkeypatch.setenv("BIC_CLUSTER_THREADS", "512")
+    assert np.array_equal(run(), clustered)
+    monkeypatch.delenv("BIC_CLUSTER_THREADS")
+    monkeypatch.setenv("BIC_CLUSTER_SIZE", "8")
+    assert np.array_equal(run(), clustered)
+    monkeypatch.delenv("BIC_CLUSTER_SIZE")
+    monkeypatch.setenv("BIC_CLUSTER", "0")
+    assert np.array_equal(run(), clustered)                   # sub-range passes
     monkeypatch.setenv("BIC_RANGE_PASSES", "0")
-    with pkg.BicScorer(codes, card) as s:
-        tabs0 = s.count_families([f[0] for f in fams], [f[1] for f in fams])
-        for t, t0 in zip(tabs, tabs0):
-            assert np.array_equal(t, t0)
-        assert np.array_equal(s.score_families_csr(node, off, par, no_cache=True), ranged)
+    assert np.array_equal(run(), clustered)                   # L2 atomics
 
 
 def test_slice_choice_does_not_change_bits(monkeypatch):

@@ -29,7 +29,7 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(nat.SYMBOLS), declared ^ set(nat.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bic_version() == 100
+    assert lib.bic_version() == 200
 
 
 def test_library_is_sm100a_only():
@@ -91,7 +91,47 @@ def test_wire_roundtrip_against_oracle(known_answer, golden_dir):
     for b, row in enumerate(rows):
         assert np.array_equal(adj[b], O.labeled_dict_to_adjacency(row, 8))
     fixture = np.load(os.path.join(golden_dir, "asia_candidates_10k.npz"))
-    assert np.array_equal(fixture["labels"][:64], labels) and np.array_equal(fixture["ebits"][:64], ebits)
+    assert np.array_equal(fixture["labels"][:64], labels) and np.array_equal(fixture["ebits"][:64], ebits[:, :, 0])
+
+
+def test_wire_any_n_and_decoder_adapter_cpu():
+    """Host logic of rows a8 / f2 / f3 without a GPU: multi-word edge masks and uint16 labels
+    round-trip for n > 32, and the decoder adapter's torch packing equals pack_dicts."""
+    import torch
+    from dags_vae_search_b200 import decode_adapter
+    for n in (8, 33, 70):
+        dags = synth.er_candidates(n, 40, n - 1, 2 * n, 4, seed=n)
+        labels, ebits = wire.from_adjacency(dags)
+        assert labels.dtype == np.uint16 and ebits.dtype == np.uint32 and ebits.shape == (40, n, wire.edge_words(n))
+        assert np.array_equal(wire.to_adjacency(labels, ebits), dags)
+        dicts = [{**{f"l{i}": int(labels[b, i]) for i in range(n)},
+                  **{f"e{i}": "".join(str((int(ebits[b, i, u >> 5]) >> (u & 31)) & 1) for u in range(i)) for i in range(n)}}
+                 for b in range(40)]
+        l2, e2 = wire.pack_dicts(dicts, n)
+        assert np.array_equal(l2, labels) and np.array_equal(e2, ebits)
+        # decoder-shaped tensors: PACE types (label + 3) and lower-triangular edge draws
+        draws = np.zeros((40, n, n), dtype=bool)
+        for b in range(40):
+            for i in range(n):
+                for u in range(i):
+                    draws[b, i, u] = (int(ebits[b, i, u >> 5]) >> (u & 31)) & 1
+        draws_noise = draws | np.triu(np.ones((n, n), dtype=bool))          # u >= v must be ignored
+        lt, et = decode_adapter.decoded_to_wire(torch.from_numpy(labels.astype(np.int64) + 3), torch.from_numpy(draws_noise), n)
+        assert np.array_equal(lt.numpy(), labels.astype(np.int32))
+        assert np.array_equal(et.numpy().view(np.uint32), ebits)
+        bad = labels.astype(np.int64) + 3
+        bad[0, 0] = 1                                                        # output node as a vertex type
+        lt, _ = decode_adapter.decoded_to_wire(torch.from_numpy(bad), torch.from_numpy(draws), n)
+        assert lt[0, 0] == 65535
+    # labels outside uint16 never wrap into range
+    l3, _ = wire.pack_dicts([{"l0": 70000, "l1": 1, "e0": "", "e1": "0"}], 2)
+    assert l3[0, 0] == 65535
+    st = decode_adapter.DecodeState(5, 4, "cpu")
+    for idx in range(2, 6):
+        t = st.step(idx, torch.zeros(5, 7), torch.ones(5, idx - 1, 1), force_type=idx + 1)
+        assert (t == idx + 1).all()
+    lab, eb = st.wire()
+    assert lab.tolist() == [[0, 1, 2, 3]] * 5 and eb[:, :, 0].tolist() == [[0, 1, 3, 7]] * 5    # every earlier vertex is a parent
 
 
 def test_synth_candidates_are_dags():
@@ -220,7 +260,7 @@ def test_launch_plan_rules(monkeypatch):
     """bic_plan_slices is the host arithmetic the library uses to cut a batch of new families into
     count-kernel work items (csrc/bicgpu.cu:plan_count).  It never changes a result, only the time,
     so what is pinned here are its rules, on the shapes of the BASELINE configs."""
-    for v in ("BIC_SLICE_MODEL", "BIC_RANGE_PASSES", "BIC_L2_WINDOW_MB", "BIC_L2_WINDOW_MAX_MB"):
+    for v in ("BIC_SLICE_MODEL", "BIC_RANGE_PASSES", "BIC_L2_WINDOW_MB", "BIC_L2_WINDOW_MAX_MB", "BIC_CLUSTER", "BIC_CLUSTER_SIZE"):
         monkeypatch.delenv(v, raising=False)
     MB = 1 << 20
 
@@ -238,11 +278,20 @@ def test_launch_plan_rules(monkeypatch):
     assert 148 * 4 // 40 <= few["slices"][0] <= 4 * 148 * 4 // 40
 
     # diabetes-shaped local moves (5.2 GB of rows): the few large-table families are not cut into
-    # 162 L2 windows (their merges would cost more than the counting), class 3 runs in 4 passes
+    # 162 L2 windows (their merges would cost more than the counting); class 3 (194 481 cells) runs
+    # in one pass over clusters of 4 CTAs, or in 4 sub-range passes with BIC_CLUSTER=0
     N = 12_500_000
     fams = [(2, 600)] * 240 + [(2, 6000)] * 99 + [(3, 30000)] * 33 + [(3, 194481)] * 7
     diab = nat.plan_slices(N, 413, fams, tables_in_hbm=True)
-    assert diab["ranged"] and diab["passes"] == 4
+    assert diab["cluster"] == 4 and not diab["ranged"] and diab["slices"][3] <= N // (4 * 194481)
+    monkeypatch.setenv("BIC_CLUSTER_SIZE", "8")
+    assert nat.plan_slices(N, 413, fams, tables_in_hbm=True)["cluster"] == 8
+    monkeypatch.delenv("BIC_CLUSTER_SIZE")
+    assert nat.plan_slices(N, 20, [(8, 49152 * 8)])["cluster"] == 8 and nat.plan_slices(N, 20, [(3, 49153)])["cluster"] == 2
+    assert nat.plan_slices(N, 20, [(8, 49152 * 8 + 1)])["cluster"] == 0      # beyond 8 x 192 KB of distributed shared memory
+    monkeypatch.setenv("BIC_CLUSTER", "0")
+    diab = nat.plan_slices(N, 413, fams, tables_in_hbm=True)
+    assert diab["ranged"] and diab["passes"] == 4 and diab["cluster"] == 0
     assert diab["slices"][1] < 20 and diab["slices"][2] < 10 and diab["slices"][3] <= N // (4 * 194481)
     assert windows(413, N, 256) <= diab["slices"][0] < windows(413, N, 32)      # all resident at once: wide windows
     pigs = nat.plan_slices(N, 441, [(2, 81)] * 391, tables_in_hbm=True)
@@ -263,6 +312,7 @@ def test_launch_plan_rules(monkeypatch):
     monkeypatch.setenv("BIC_RANGE_PASSES", "0")
     assert not nat.plan_slices(N, 413, fams)["ranged"]
     monkeypatch.delenv("BIC_RANGE_PASSES")
+    monkeypatch.delenv("BIC_CLUSTER")
 
     # argument checks
     bad = nat.PlanIn(sm_count=0, N=10, n=2)
