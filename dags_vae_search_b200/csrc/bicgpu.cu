@@ -691,6 +691,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
             long long counted_cells = 0;
             for (int k = 0; k < NCLASS; ++k) counted_cells += (long long)h.class_cells[k];
             c->prof.exchange_bytes += counted_cells * 4 * (c->world - 1) / c->world;   // what this rank stores into peers' buffers
+            k_sum_slots<<<c->sm_count * 4, 256, 0, c->stream>>>(c->xchg, c->xcap, c->world, c->rank_id, c->d_hdr); LAUNCH(c);
         } else {
             size_t cells = (size_t)h.cells_all;   // all tables live in HBM when sharded: exact
             if (cells) {

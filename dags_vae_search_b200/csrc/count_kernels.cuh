@@ -431,18 +431,16 @@ constexpr u32 STAGE_WORDS = 6144;   // staging buffer of the kernels that reduce
 // block with coalesced, independent loads: one CTA walking a 200 k-cell table with dependent
 // 4-byte loads (the first version) spent ~150 us in L2 latency per family.  The order in which a
 // lane meets its configurations is the same either way.
-// Source of an HBM table: one table, or (row-sharded runs with the fused reduce-scatter) the sum of
-// `nsrc` partial tables `sstride` cells apart — the slots the ranks pushed into this rank's exchange
-// buffer; `wb` (nullable) receives the summed table (donors of derived families need it in the arena).
+// HBM-table reduce options: `wb` (nullable) also receives a copy of the table as it streams
+// through shared memory (row-sharded runs: the owner's summed table goes back into the arena when
+// derived families need it as their donor).
 struct TabSrc {
-    int nsrc;
-    size_t sstride;
     u32 *wb;
 };
 
 template <bool FROM_GLOBAL, class RowFn>
 __device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap, RowFn row,
-                                              TabSrc ts = TabSrc{1, 0, nullptr}) {
+                                              TabSrc ts = TabSrc{nullptr}) {
     double acc[2] = {0.0, 0.0};
     if (!FROM_GLOBAL) {
 #pragma unroll
@@ -458,31 +456,22 @@ __device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, doub
             const u32 *src = tab + (size_t)base * r;
             __syncthreads();          // the previous piece has been consumed
             u32 i = threadIdx.x;
-            if (ts.nsrc == 1 && !ts.wb) {
-                for (; i + 7 * blockDim.x < ncell; i += 8 * blockDim.x) {
-                    u32 v[8];
+            u32 *wb = ts.wb ? ts.wb + (size_t)base * r : nullptr;
+            for (; i + 7 * blockDim.x < ncell; i += 8 * blockDim.x) {
+                u32 v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __ldcg(src + i + e * blockDim.x);
+                for (int e = 0; e < 8; ++e) v[e] = __ldcg(src + i + e * blockDim.x);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) stage[i + e * blockDim.x] = v[e];
+                for (int e = 0; e < 8; ++e) stage[i + e * blockDim.x] = v[e];
+                if (wb) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) wb[i + e * blockDim.x] = v[e];
                 }
-                for (; i < ncell; i += blockDim.x) stage[i] = __ldcg(src + i);
-            } else {
-                // the partial tables of all ranks: nsrc independent loads per cell, two cells in flight
-                for (; i < ncell; i += 2 * blockDim.x) {
-                    const u32 i2 = i + blockDim.x;
-                    u32 v0 = 0, v1 = 0;
-                    for (int s2 = 0; s2 < ts.nsrc; ++s2) {
-                        v0 += __ldcg(src + (size_t)s2 * ts.sstride + i);
-                        if (i2 < ncell) v1 += __ldcg(src + (size_t)s2 * ts.sstride + i2);
-                    }
-                    stage[i] = v0;
-                    if (i2 < ncell) stage[i2] = v1;
-                    if (ts.wb) {
-                        ts.wb[(size_t)base * r + i] = v0;
-                        if (i2 < ncell) ts.wb[(size_t)base * r + i2] = v1;
-                    }
-                }
+            }
+            for (; i < ncell; i += blockDim.x) {
+                const u32 v = __ldcg(src + i);
+                stage[i] = v;
+                if (wb) wb[i] = v;
             }
             __syncthreads();
 #pragma unroll
@@ -514,7 +503,7 @@ __device__ __forceinline__ double reduce_rows(const u32 *tab, u32 q, int r, doub
 // sum_{j,x: c>0} c * ln(c / N_ij)
 template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, double *sh, u32 *stage, u32 cap,
-                                                TabSrc ts = TabSrc{1, 0, nullptr}) {
+                                                TabSrc ts = TabSrc{nullptr}) {
     return reduce_rows<FROM_GLOBAL>(tab, q, r, sh, stage, cap, [r](const u32 *row, double &acc) {
         u32 nij = 0;
         for (int x = 0; x < r; ++x) nij += row[x];
@@ -532,7 +521,7 @@ __device__ __forceinline__ double family_loglik(const u32 *tab, u32 q, int r, do
 // sum_j [ lgamma(a_ij) - lgamma(a_ij + N_ij) + sum_x ( lgamma(a_ijk + c) - lgamma(a_ijk) ) ].
 template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double a_ij, double a_ijk, double *sh,
-                                            u32 *stage, u32 cap, TabSrc ts = TabSrc{1, 0, nullptr}) {
+                                            u32 *stage, u32 cap, TabSrc ts = TabSrc{nullptr}) {
     const double lg_ij = lgamma(a_ij), lg_ijk = lgamma(a_ijk);
     return reduce_rows<FROM_GLOBAL>(tab, q, r, sh, stage, cap, [=](const u32 *row, double &acc) {
         u32 nij = 0;
@@ -550,7 +539,7 @@ __device__ __forceinline__ double family_bd(const u32 *tab, u32 q, int r, double
 // FROM_GLOBAL: `stage` / `cap` = shared-memory staging buffer (see reduce_rows).
 template <bool FROM_GLOBAL>
 __device__ __forceinline__ double family_term(const CountArgs &a, const u32 *tab, const FamMeta &m, double *sh,
-                                              u32 *stage = nullptr, u32 cap = 0, TabSrc ts = TabSrc{1, 0, nullptr}) {
+                                              u32 *stage = nullptr, u32 cap = 0, TabSrc ts = TabSrc{nullptr}) {
     if (a.bd_mode == 0) return family_loglik<FROM_GLOBAL>(tab, m.q, m.r, sh, stage, cap, ts);
     double a_ijk = a.bd_mode == 1 ? a.iss / ((double)m.q * (double)m.r) : 1.0;
     return family_bd<FROM_GLOBAL>(tab, m.q, m.r, a_ijk * (double)m.r, a_ijk, sh, stage, cap, ts);
@@ -823,10 +812,27 @@ __global__ void __launch_bounds__(THREADS) k_count_cluster(CountArgs a, int CL) 
     }
 }
 
+// Owner side of the fused reduce-scatter: slot `rank` of the own exchange buffer becomes the sum of
+// all `world` slots over the cells this rank owns (the tables lie back to back, so this is one
+// element-wise pass, 16 bytes per thread-iteration).  Runs after the barrier that orders every
+// rank's peer stores.
+__global__ void __launch_bounds__(256) k_sum_slots(u32 *xchg, u64 xcap, int world, int rank, const Header *hdr) {
+    const u64 nvec = (hdr->owned_max + 3) >> 2;   // upper bound of this rank's owned cells (tables are 4-cell aligned)
+    uint4 *dst = reinterpret_cast<uint4 *>(xchg + (size_t)rank * xcap);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (u64)gridDim.x * blockDim.x) {
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (int s = 0; s < world; ++s) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(xchg + (size_t)s * xcap) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        dst[i] = acc;
+    }
+}
+
 // k3 alone: reduce HBM tables of a row-sharded run.  Without the fused reduce-scatter (world 1, the
 // caller wants every table, or the exchange buffer is too small) every rank holds the all-reduced
 // tables in its arena and reduces all of them.  With it (a.push) a rank reduces only the families it
-// owns, from the `world` partial tables the ranks pushed into its exchange buffer.
+// owns, from the sum of the `world` partial tables the ranks pushed into its exchange buffer.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njobs) {
     __shared__ FamMeta m;
@@ -839,9 +845,9 @@ __global__ void __launch_bounds__(THREADS) k_reduce_tables(CountArgs a, int njob
     if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
     __syncthreads();
     double ll;
-    if (a.push) {
-        TabSrc ts{a.world, (size_t)a.xcap, a.writeback ? a.arena + a.table_off[j] : nullptr};
-        ll = family_term<true>(a, a.peer[a.rank] + a.xoff[j], m, s_red, s_stage, STAGE_WORDS, ts);
+    if (a.push) {   // slot `rank` of the own exchange buffer holds the sum over all ranks (k_sum_slots)
+        TabSrc ts{a.writeback ? a.arena + a.table_off[j] : nullptr};
+        ll = family_term<true>(a, a.peer[a.rank] + (size_t)a.rank * a.xcap + a.xoff[j], m, s_red, s_stage, STAGE_WORDS, ts);
     } else {
         ll = family_term<true>(a, a.arena + a.table_off[j], m, s_red, s_stage, STAGE_WORDS);
     }
