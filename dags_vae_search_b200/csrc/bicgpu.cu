@@ -138,6 +138,7 @@ struct bic_ctx {
         int cluster = 1;                       // BIC_CLUSTER=0: class 3 in sub-range passes instead of one pass over a thread-block cluster
         int cluster_size = 0;                  // BIC_CLUSTER_SIZE: force 2, 4 or 8 CTAs per cluster (0: smallest that holds the table)
         int cluster_threads = 1024;            // BIC_CLUSTER_THREADS: 512 or 1024
+        bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
                                                //   fused reduce-scatter over peer memory
         long long xchg_mb = 64;                // BIC_XCHG_MB: exchange-buffer slot per source rank (MB)
@@ -157,6 +158,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER")) cluster = atoi(e) != 0;
             if (const char *e = getenv("BIC_CLUSTER_SIZE")) { int v = atoi(e); if (v == 0 || v == 2 || v == 4 || v == 8) cluster_size = v; }
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
+            if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
             if (const char *e = getenv("BIC_NO_PUSH")) push = atoi(e) == 0;
             if (const char *e = getenv("BIC_PUSH_WORLD1")) push_world1 = atoi(e) != 0;
             if (const char *e = getenv("BIC_XCHG_MB")) { long long v = atoll(e); if (v > 0 && v <= 4096) xchg_mb = v; }
@@ -605,6 +607,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.donor = (with_donors && n_derived) ? c->donor.as<int>() : nullptr;
     a.bd_mode = c->cache_mode;
     a.p2_vec = c->tune.p2_vec;
+    a.tma = c->tune.tma ? 1 : 0;
     a.iss = c->iss;
     a.push = push ? 1 : 0;
     a.rank = c->rank_id; a.world = c->world;
@@ -648,10 +651,11 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
         const u32 clwords = clustered ? (u32)((max_cells + CL - 1) / CL) : 0;
         a.stage_words = k == 3 ? (clustered ? clwords : ranged ? span : GLOBAL_STAGE) : cap[k];
-        if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32))));
-        if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
+        const size_t ring256 = a.tma ? tma_ring_bytes(256) : 0, ring512 = a.tma ? tma_ring_bytes(512) : 0;   // TMA staging ring behind the table
+        if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32) + ring256)));
+        if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32) + ring512)));
         if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));
-        if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32))));
+        if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32) + ring512)));
         const bool wide = c->tune.class2_threads == 1024;
         if (k == 2 && !wide) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 2 && wide) TRY((launch_count<1024, false>(c, a, items, cap[2] * sizeof(u32))));

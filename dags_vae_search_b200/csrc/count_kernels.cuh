@@ -41,6 +41,7 @@ struct CountArgs {
     double *np_out;          // (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
+    int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
     int p2_vec;              // packed path: 32-bit words of a column one thread loads per iteration (4, 2 or 1)
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
     double iss;
@@ -246,6 +247,151 @@ __device__ __forceinline__ void count_rows_mode(const FamMeta &m, const uint8_t 
         case MODE_U8: count_rows_k<K, MODE_U8, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist); break;
         case MODE_U16: count_rows_k<K, MODE_U16, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist); break;
         default: count_rows_k<K, MODE_U32, GLOBAL, THREADS>(m, data, stride, N, v0, v1, hist); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA-staged row tiles (experiment knob BIC_TMA=1, uint8 path of classes 0 and 1).  One elected
+// thread streams the k+1 column segments of a tile into a shared-memory ring with bulk copies
+// (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier; all threads read their 8 rows per
+// column back with LDS.64.  The copies land in shared memory without passing through L1, so the
+// in-flight rows no longer compete with the lane-replicated tables for the SM's unified
+// L1 / shared memory; the read-back costs the same data-pipe wavefronts as the load return it
+// replaces (see DESIGN.md for the measured outcome).
+constexpr int TMA_STAGES = 2;
+constexpr int TMA_NW = 2;                        // 32-bit words (4 rows each) per thread per column per tile
+constexpr int TMA_MAXCOLS = 7;
+__host__ __device__ constexpr u32 tma_ring_bytes(int threads) { return (u32)(TMA_STAGES * TMA_MAXCOLS * threads * 4 * TMA_NW); }
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n TMA_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra TMA_DONE;\n bra TMA_WAIT;\n "
+        "TMA_DONE:\n}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// cell byte offsets of 4 * NW consecutive rows from NW words per column (the word-count-generic
+// forms of cells_u8 / cells_u16 / cells_u32 above)
+template <int K, int NW, int MODE>
+__device__ __forceinline__ void cells_words(const u32 (&w)[K + 1][NW], const u32 (&rad)[K + 1], u32 mul, u32 (&off)[4 * NW]) {
+    if (MODE == MODE_U8) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            u32 acc = w[0][i];
+#pragma unroll
+            for (int a = 1; a <= K; ++a) acc = acc * rad[a] + w[a][i];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) off[i * 4 + b] = __byte_perm(acc, 0u, 0x4440u + b) * mul;
+        }
+    } else if (MODE == MODE_U16) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            u32 lo = 0, hi = 0;
+#pragma unroll
+            for (int a = 0; a <= K; ++a) {
+                const u32 l = __byte_perm(w[a][i], 0u, 0x4140u), h = __byte_perm(w[a][i], 0u, 0x4342u);
+                lo = a == 0 ? l : lo * rad[a] + l;
+                hi = a == 0 ? h : hi * rad[a] + h;
+            }
+            lo *= mul;
+            hi *= mul;
+            off[i * 4 + 0] = lo & 0xffffu; off[i * 4 + 1] = lo >> 16;
+            off[i * 4 + 2] = hi & 0xffffu; off[i * 4 + 3] = hi >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                u32 c = 0;
+#pragma unroll
+                for (int a = 0; a <= K; ++a) c = c * rad[a] + ((w[a][i] >> (8 * b)) & 0xffu);
+                off[i * 4 + b] = c * mul;
+            }
+    }
+}
+
+// [v0, v1): the CTA's slice in 16-row vectors; ring: TMA_STAGES x (K + 1) tiles of THREADS * 4 * NW bytes
+template <int K, int MODE, int THREADS>
+__device__ __forceinline__ void count_rows_tma(const FamMeta &m, const uint8_t *__restrict__ data, long long stride, long long N,
+                                               long long v0, long long v1, u32 *hist, uint8_t *ring, u64 *full) {
+    constexpr int NW = TMA_NW, C = K + 1;
+    constexpr u32 TILE = THREADS * 4 * NW;                 // bytes (= rows) of one column segment
+    const uint8_t *cp[C];
+    u32 rad[C];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    const u32 mul = m.mul;
+    const long long r0 = v0 * 16, r1 = v1 * 16;            // 16-byte granularity: r1 may exceed N inside the padded stride
+    const long long ntiles = (r1 - r0 + TILE - 1) / TILE;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long t) {
+        const int s = (int)(t % TMA_STAGES);
+        const long long rb = r0 + t * TILE;
+        const u32 bytes = (u32)min((long long)TILE, r1 - rb);
+        mbar_expect_tx(&full[s], bytes * C);
+#pragma unroll
+        for (int a = 0; a < C; ++a) bulk_g2s(ring + ((size_t)s * C + a) * TILE, cp[a] + rb, bytes, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (long long t = 0; t < TMA_STAGES - 1 && t < ntiles; ++t) issue(t);
+    for (long long t = 0; t < ntiles; ++t) {
+        const int s = (int)(t % TMA_STAGES);
+        if (threadIdx.x == 0 && t + TMA_STAGES - 1 < ntiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the stage are ordered before its refill
+            issue(t + TMA_STAGES - 1);
+        }
+        mbar_wait(&full[s], (u32)((t / TMA_STAGES) & 1));
+        const long long row = r0 + t * TILE + (long long)threadIdx.x * (4 * NW);
+        if (row < N) {
+            u32 w[C][NW];
+#pragma unroll
+            for (int a = 0; a < C; ++a) {
+                const uint2 x = *reinterpret_cast<const uint2 *>(ring + ((size_t)s * C + a) * TILE + threadIdx.x * (4 * NW));
+                w[a][0] = x.x;
+                w[a][1] = x.y;
+            }
+            u32 off[4 * NW];
+            cells_words<K, NW, MODE>(w, rad, mul, off);
+            const int nv = row + 4 * NW <= N ? 4 * NW : (int)(N - row);
+#pragma unroll
+            for (int b = 0; b < 4 * NW; ++b)
+                if (b < nv) bump_off<false>(hist, off[b]);
+        }
+        __syncthreads();   // everyone is done with stage s before it is refilled
+    }
+}
+
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_tma_mode(const FamMeta &m, const uint8_t *__restrict__ data, long long stride, long long N,
+                                                    long long v0, long long v1, u32 *hist, uint8_t *ring, u64 *full) {
+    switch (count_mode(m.cells, m.R)) {
+        case MODE_U8: count_rows_tma<K, MODE_U8, THREADS>(m, data, stride, N, v0, v1, hist, ring, full); break;
+        case MODE_U16: count_rows_tma<K, MODE_U16, THREADS>(m, data, stride, N, v0, v1, hist, ring, full); break;
+        default: count_rows_tma<K, MODE_U32, THREADS>(m, data, stride, N, v0, v1, hist, ring, full); break;
     }
 }
 
@@ -573,10 +719,11 @@ __device__ __forceinline__ void push_table(const CountArgs &a, int j, const u32 
 template <int THREADS, bool GLOBAL, bool RANGE = false>
 __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) k_count(CountArgs a) {   // 64 registers: 1024 threads per SM
     static_assert(!(GLOBAL && RANGE), "a sub-range table lives in shared memory");
-    extern __shared__ u32 s_hist[];
+    extern __shared__ __align__(128) u32 s_hist[];
     __shared__ FamMeta m;
     __shared__ double s_red[32];
     __shared__ int s_last;
+    __shared__ __align__(8) u64 s_full[TMA_STAGES];
 
     // slice-major item order: the CTAs resident at any moment work on the same row window of
     // the dataset, which the host sizes to stay L2-resident
@@ -630,6 +777,17 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
         if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist);
         else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist);
         else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+    } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.tma && m.k <= 6) {
+        uint8_t *ring = reinterpret_cast<uint8_t *>(s_hist + a.cap_words);
+        switch (m.k) {
+            case 0: count_rows_tma_mode<0, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+            case 1: count_rows_tma_mode<1, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+            case 2: count_rows_tma_mode<2, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+            case 3: count_rows_tma_mode<3, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+            case 4: count_rows_tma_mode<4, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+            case 5: count_rows_tma_mode<5, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+            default: count_rows_tma_mode<6, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, ring, s_full); break;
+        }
     } else
     switch (m.k) {
         case 0: count_rows_mode<0, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;

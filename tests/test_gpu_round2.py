@@ -369,3 +369,29 @@ def test_bench_synthetic_v12_c2_batch():
         fams = [(int(i), [int(p) for p in np.flatnonzero(dags[b][:, i])]) for b in range(40) for i in (0, 5, 11)]
         for (i, ps), t in zip(fams, s.count_families([f[0] for f in fams], [f[1] for f in fams])):
             assert np.array_equal(t, O.family_counts(host, card, i, ps))
+
+
+# ------------------------------------------- TMA-staged row tiles (experiment knob BIC_TMA=1)
+@pytest.mark.parametrize("N", [1, 15, 2047, 2048, 2049, 70_001, 600_000])
+def test_tma_staged_tiles_match_default_path(N, monkeypatch):
+    """uint8 path of classes 0 / 1 with the rows staged through a shared-memory ring by bulk copies
+    (cp.async.bulk + mbarrier): identical counts and score bits; ragged tails, 1..7 columns, all
+    three lane modes, a family the ring does not serve (class 2) in the same call."""
+    rng = np.random.default_rng(N)
+    card = np.array([2, 3, 4, 5, 3, 2, 7, 6, 1, 3, 9, 11], dtype=np.int32)
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    fams = [(0, []), (1, [0]), (2, [0, 1]), (3, [0, 1, 2]), (4, [0, 1, 2, 3]), (5, [0, 1, 2, 3, 4]),
+            (9, [0, 1, 2, 3, 4, 5]), (6, [1, 3, 7]), (7, [2, 3]), (3, [8, 9]), (2, [3, 4, 6, 9]),
+            (10, [6, 7, 11]), (11, [3, 6, 7, 10]), (0, [1, 2, 4, 5, 8, 9, 3])]
+    node = np.array([f[0] for f in fams], dtype=np.int32)
+    off = np.zeros(len(fams) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(f[1]) for f in fams])
+    par = np.array([p for f in fams for p in f[1]], dtype=np.int32)
+    with pkg.BicScorer(codes, card) as s:
+        want = s.score_families_csr(node, off, par, no_cache=True)
+    monkeypatch.setenv("BIC_TMA", "1")
+    with pkg.BicScorer(codes, card) as s:
+        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+        for (i, ps), t in zip(fams, tabs):
+            assert np.array_equal(t, O.family_counts(codes, card, i, ps)), (N, i, ps)
+        assert np.array_equal(s.score_families_csr(node, off, par, no_cache=True), want)
