@@ -366,7 +366,7 @@ __device__ __forceinline__ void count_rows_tma(const FamMeta &m, const uint8_t *
         }
         mbar_wait(&full[s], (u32)((t / TMA_STAGES) & 1));
         const long long row = r0 + t * TILE + (long long)threadIdx.x * (4 * NW);
-        if (row < N) {
+        if (row < N && row < r1) {   // the last tile of a slice is partly filled: what lies beyond r1 is another slice's
             u32 w[C][NW];
 #pragma unroll
             for (int a = 0; a < C; ++a) {
@@ -705,8 +705,16 @@ __device__ __forceinline__ void slice_blocks(long long N, int slice, int S, long
 // slot `rank` of the owner rank's exchange buffer with coalesced peer stores over NVLink.
 template <int THREADS, bool FROM_SHARED>
 __device__ __forceinline__ void push_table(const CountArgs &a, int j, const u32 *src, u32 cells) {
-    u32 *dst = a.peer[a.owner[j]] + (size_t)a.rank * a.xcap + a.xoff[j];
-    for (u32 c = threadIdx.x; c < cells; c += THREADS) dst[c] = FROM_SHARED ? src[c] : __ldcg(src + c);
+    u32 *dst = a.peer[a.owner[j]] + (size_t)a.rank * a.xcap + a.xoff[j];   // 16-byte aligned (k_owner_offsets)
+    if (FROM_SHARED) {   // the shared-memory table starts 16-byte aligned: 16 bytes per store, 512 per warp
+        const u32 n4 = cells >> 2;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (u32 c = threadIdx.x; c < n4; c += THREADS) d4[c] = s4[c];
+        for (u32 c = (n4 << 2) + threadIdx.x; c < cells; c += THREADS) dst[c] = src[c];
+    } else {
+        for (u32 c = threadIdx.x; c < cells; c += THREADS) dst[c] = __ldcg(src + c);
+    }
 }
 
 // RANGE (class 3 when the rows dwarf the table): the table does not fit one CTA's shared memory,

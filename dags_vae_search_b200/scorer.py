@@ -357,7 +357,7 @@ class BicScorer:
         out = {}
         for k, _ in nat.Profile._fields_:
             v = getattr(p, k)
-            out[k] = list(v) if hasattr(v, "__len__") else (float(v) if k == "count_ms" else int(v))
+            out[k] = list(v) if hasattr(v, "__len__") else (float(v) if k.endswith("_ms") else int(v))
         return out
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
