@@ -631,6 +631,7 @@ def main():
             res = {"ms_per_step": ms_r / rsteps, "dags_per_s": rbatch * rsteps / (ms_r * 1e-3),
                    "count_ms_per_step": pr["count_ms"] / rsteps, "exchange_ms_per_step": pr["exchange_ms"] / rsteps,
                    "exchange_bytes_per_step": pr["exchange_bytes"] / rsteps, "kernel_launches_per_step": pr["kernel_launches"] / rsteps,
+                   "exchange_steps_fused": pr["exchange_fused"], "exchange_steps_nccl": pr["exchange_nccl"],
                    "families_counted_per_step": pr["families_counted"] / rsteps, "families_derived_per_step": pr["families_derived"] / rsteps,
                    "family_count_rows_per_sec_per_gpu": pr["rows_counted"] / (pr["count_ms"] * 1e-3) if pr["count_ms"] > 0 else None}
             if mode == "fused":
@@ -772,7 +773,8 @@ def main():
         "checksum": checksum,
     }
     if sharded:
-        line["row_exchange"] = {"exchange_ms_per_step": prof["exchange_ms"] / args.steps, "exchange_bytes_per_step": prof["exchange_bytes"] / args.steps}
+        line["row_exchange"] = {"exchange_ms_per_step": prof["exchange_ms"] / args.steps, "exchange_bytes_per_step": prof["exchange_bytes"] / args.steps,
+                                "exchange_steps_fused": prof["exchange_fused"], "exchange_steps_nccl": prof["exchange_nccl"]}
     if stream_leg:
         line["stream_1m"] = stream_leg
     if world > 1:

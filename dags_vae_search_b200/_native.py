@@ -91,7 +91,7 @@ class Profile(ctypes.Structure):
                 ("class_ms", ctypes.c_double * 4), ("class_launches", ctypes.c_int64 * 4),
                 ("class_families", ctypes.c_int64 * 4), ("class_alg_bytes", ctypes.c_int64 * 4),
                 ("families_derived", ctypes.c_int64), ("exchange_ms", ctypes.c_double),
-                ("exchange_bytes", ctypes.c_int64)]
+                ("exchange_bytes", ctypes.c_int64), ("exchange_fused", ctypes.c_int64), ("exchange_nccl", ctypes.c_int64)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

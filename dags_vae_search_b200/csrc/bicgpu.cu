@@ -101,6 +101,7 @@ struct bic_ctx {
     // dataset
     uint8_t *data = nullptr;
     uint8_t *data2 = nullptr;    // 2-bit packed shadow copy (columns with <= 4 states), stride2 = stride / 4
+    bool all_packed = false;     // every column has one: all families stream the packed copy
     long long stride2 = 0;
     long long N = 0, stride = 0, N_total = 0;
     int n = 0, W64 = 0, Wk = 0;
@@ -129,13 +130,14 @@ struct bic_ctx {
         long long derive_min_rows = 1ll << 20;
         long long l2_window = 32ll << 20;      // BIC_L2_WINDOW_MB: dataset bytes of one row slice kept L2-resident
         long long l2_window_max = 256ll << 20; // BIC_L2_WINDOW_MAX_MB: window when all families of a class are resident at once
-        u32 class0_words = CLASS0_WORDS;       // BIC_CLASS0_WORDS: shared-memory words of a class-0 CTA
+        u32 class0_words = CLASS0_WORDS;       // BIC_CLASS0_WORDS: shared-memory words of a class-0 CTA (uint8 path)
+        u32 class0_words_packed = CLASS0_WORDS_PACKED;   // the same when every column streams from the 2-bit packed copy
         int class0_threads = 256;              // BIC_CLASS0_THREADS: 256, 512 or 1024
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
                                                //   are counted in passes (0: always straight into HBM with L2 atomics)
         int class2_threads = 1024;             // BIC_CLASS2_THREADS: 512 or 1024 (classes 2 and 3-in-passes: one CTA per SM)
         int p2_vec = 4;                        // BIC_P2_VEC: 32-bit words of a packed column per thread-iteration (4, 2 or 1)
-        int cluster = 1;                       // BIC_CLUSTER=0: class 3 in sub-range passes instead of one pass over a thread-block cluster
+        int cluster = 0;                       // BIC_CLUSTER=1: class 3 in one pass over a thread-block cluster (measured 3x slower than sub-range passes)
         int cluster_size = 0;                  // BIC_CLUSTER_SIZE: force 2, 4 or 8 CTAs per cluster (0: smallest that holds the table)
         int cluster_threads = 1024;            // BIC_CLUSTER_THREADS: 512 or 1024
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
@@ -151,7 +153,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
             if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
             if (const char *e = getenv("BIC_L2_WINDOW_MAX_MB")) { long long mb = atoll(e); if (mb > 0) l2_window_max = mb << 20; }
-            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 16384) class0_words = (u32)w; }
+            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 49152) { class0_words = (u32)w; class0_words_packed = (u32)w; } }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
             if (const char *e = getenv("BIC_P2_VEC")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) p2_vec = v; }
@@ -646,7 +648,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         // shared memory per CTA: class 0 gets several times its largest table so that small tables
         // run with 32 or 16 bank-interleaved lane replicas (conflict-free atomics).
         const int c0t = c->tune.class0_threads;
-        const u32 cap[NCLASS] = {c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
+        const u32 cap[NCLASS] = {c->all_packed ? c->tune.class0_words_packed : c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
         const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
         const u32 clwords = clustered ? (u32)((max_cells + CL - 1) / CL) : 0;
@@ -695,6 +697,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
             long long counted_cells = 0;
             for (int k = 0; k < NCLASS; ++k) counted_cells += (long long)h.class_cells[k];
             c->prof.exchange_bytes += counted_cells * 4 * (c->world - 1) / c->world;   // what this rank stores into peers' buffers
+            ++c->prof.exchange_fused;
             k_sum_slots<<<c->sm_count * 4, 256, 0, c->stream>>>(c->xchg, c->xcap, c->world, c->rank_id, c->d_hdr); LAUNCH(c);
         } else {
             size_t cells = (size_t)h.cells_all;   // all tables live in HBM when sharded: exact
@@ -703,6 +706,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
                 if (rc != 0) return fail(c, BIC_ERR_NCCL, "ncclAllReduce(count tables): " + nccl_err(rc));
             }
             c->prof.exchange_bytes += (long long)cells * 4;
+            ++c->prof.exchange_nccl;
         }
         k_reduce_tables<256><<<(unsigned)njobs, 256, 0, c->stream>>>(a, (int)njobs); LAUNCH(c);
         CU(cudaGetLastError());
@@ -1201,7 +1205,10 @@ int bic_set_dataset(bic_ctx *c, const uint8_t *codes, int64_t N, int32_t n, int6
     // measured: at 100 k rows the packed path is 1.7x SLOWER (a thread runs only ~6 iterations of a
     // long unrolled body; per-item overhead and instruction fetch dominate), at 10 M rows 1.4x faster
     c->tune.from_env();   // tests switch the packed path per dataset
+    c->all_packed = false;
     if (any_small && c->tune.pack2 && N >= c->tune.pack2_min_rows) {
+        c->all_packed = true;
+        for (int v = 0; v < n; ++v) c->all_packed = c->all_packed && card[v] <= 4;
         c->stride2 = pstride / 4;
         CU(cudaMalloc(&c->data2, (size_t)c->stride2 * n));
         CU(cudaMemsetAsync(c->data2, 0, (size_t)c->stride2 * n, c->stream));

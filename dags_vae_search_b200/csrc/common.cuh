@@ -23,6 +23,9 @@ constexpr u32 CLASS0_CELLS = 2048;         //   8 KB of int32 -> many CTAs per S
 constexpr u32 CLASS0_WORDS = 6144;         //  24 KB per class-0 CTA: room for lane replicas (count_kernels.cuh).  Swept 16..48 KB on
                                            //  B200: 24 KB is best; at 48 KB (192 KB per SM) the kernel is 15 % slower because too
                                            //  little L1 is left to land the in-flight streaming loads
+constexpr u32 CLASS0_WORDS_PACKED = 12288; //  48 KB when all families stream the 2-bit packed copy (a quarter of the bytes in flight per
+                                           //  row, so the L1 that is left suffices): 32 lane replicas up to 384 cells, 16 up to 768.
+                                           //  Swept 24..64 KB on the alarm-shaped step: 61.1 / 60.9 / 58.2 / 59.3 ms at 24 / 32 / 48 / 64 KB
 constexpr u32 CLASS1_CELLS = 12288;        //  48 KB
 constexpr u32 CLASS2_CELLS = 49152;        // 192 KB (one CTA per SM)
 

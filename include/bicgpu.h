@@ -192,6 +192,8 @@ typedef struct {
      * into peers' exchange buffers (fused reduce-scatter) or the all-reduced payload (NCCL path) */
     double exchange_ms;
     int64_t exchange_bytes;
+    int64_t exchange_fused;   /* exchange steps that took the fused reduce-scatter (peer stores) */
+    int64_t exchange_nccl;    /* exchange steps that all-reduced the tables with NCCL            */
 } bic_profile_t;
 int bic_profile_enable(bic_ctx *ctx, int on);
 int bic_profile_reset(bic_ctx *ctx);

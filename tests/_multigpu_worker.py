@@ -34,6 +34,7 @@ def main():
     lo, hi = bdist.shard_range(N, rank, world)
     s = pkg.BicScorer(np.ascontiguousarray(codes[:, lo:hi]), card, device=local)
     bdist.init_row_sharding(s)
+    s.profile_reset()
     got = s.score_adjacency(dags)
     fams = [(0, []), (3, [1]), (5, [0, 2, 7]), (9, [1, 2, 3, 4, 5, 6]), (11, [0, 1, 2, 3, 4, 5, 6, 7, 8])]
     tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
@@ -126,6 +127,7 @@ def main():
     fam.close()
     dist.barrier()
     if rank == 0:
+        print("row-sharded exchange steps: fused reduce-scatter %d, ncclAllReduce %d" % (prof_rows["exchange_fused"], prof_rows["exchange_nccl"]))
         print("multigpu ok", world)
     dist.destroy_process_group()
 

@@ -437,10 +437,10 @@ def test_packed_and_byte_paths_agree(monkeypatch):
 
 # ----------------------------------- tables above one CTA's shared memory (class 3), slicing
 def test_class3_cluster_passes_and_l2_atomics_match_oracle(monkeypatch):
-    """Tables of more than 49152 cells.  When the rows dwarf the table it is counted in ONE pass by a
+    """Tables of more than 49152 cells.  When the rows dwarf the table it is counted in passes over
+    shared-memory sub-ranges (k_count<1024,false,true>, the default) or in ONE pass by a
     thread-block cluster whose CTAs share the table in distributed shared memory (k_count_cluster,
-    the default), or in passes over shared-memory sub-ranges (k_count<1024,false,true>,
-    BIC_CLUSTER=0); otherwise straight into HBM with L2 atomics.  All three must give the oracle's
+    BIC_CLUSTER=1; measured slower); otherwise straight into HBM with L2 atomics.  All three must give the oracle's
     counts and identical score bits; ragged row count, k <= 6 (specialised row loop) and k > 6
     (generic loop), one and several row slices, cluster sizes 2 / 4 / 8."""
     N = 1_200_003
@@ -471,17 +471,18 @@ def test_class3_cluster_passes_and_l2_atomics_match_oracle(monkeypatch):
         assert_scores(scores, want_scores)
         return scores
 
-    clustered = run()
+    ranged = run()                                            # sub-range passes
+    monkeypatch.setenv("BIC_CLUSTER", "1")
+    assert np.array_equal(run(), ranged)                      # thread-block clusters
     monkeypatch.setenv("BIC_CLUSTER_THREADS", "512")
-    assert np.array_equal(run(), clustered)
+    assert np.array_equal(run(), ranged)
     monkeypatch.delenv("BIC_CLUSTER_THREADS")
     monkeypatch.setenv("BIC_CLUSTER_SIZE", "8")
-    assert np.array_equal(run(), clustered)
+    assert np.array_equal(run(), ranged)
     monkeypatch.delenv("BIC_CLUSTER_SIZE")
-    monkeypatch.setenv("BIC_CLUSTER", "0")
-    assert np.array_equal(run(), clustered)                   # sub-range passes
+    monkeypatch.delenv("BIC_CLUSTER")
     monkeypatch.setenv("BIC_RANGE_PASSES", "0")
-    assert np.array_equal(run(), clustered)                   # L2 atomics
+    assert np.array_equal(run(), ranged)                      # L2 atomics
 
 
 def test_slice_choice_does_not_change_bits(monkeypatch):

@@ -259,7 +259,7 @@ def test_exchange_buffer_path_world1(monkeypatch, derive_rows):
         got = s.score_adjacency(dags)
         prof = s.profile()
         assert np.array_equal(got, fused)
-        assert prof["exchange_ms"] > 0
+        assert prof["exchange_ms"] > 0 and prof["exchange_fused"] > 0 and prof["exchange_nccl"] == 0
         if derive_rows:
             assert prof["families_derived"] > 0
         again = s.score_adjacency(np.concatenate([dags[:50], synth.er_candidates(n, 100, n - 1, 2 * n, 5, seed=11)]))

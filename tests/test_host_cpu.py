@@ -279,9 +279,10 @@ def test_launch_plan_rules(monkeypatch):
 
     # diabetes-shaped local moves (5.2 GB of rows): the few large-table families are not cut into
     # 162 L2 windows (their merges would cost more than the counting); class 3 (194 481 cells) runs
-    # in one pass over clusters of 4 CTAs, or in 4 sub-range passes with BIC_CLUSTER=0
+    # in 4 sub-range passes, or with BIC_CLUSTER=1 in one pass over clusters of 4 CTAs
     N = 12_500_000
     fams = [(2, 600)] * 240 + [(2, 6000)] * 99 + [(3, 30000)] * 33 + [(3, 194481)] * 7
+    monkeypatch.setenv("BIC_CLUSTER", "1")
     diab = nat.plan_slices(N, 413, fams, tables_in_hbm=True)
     assert diab["cluster"] == 4 and not diab["ranged"] and diab["slices"][3] <= N // (4 * 194481)
     monkeypatch.setenv("BIC_CLUSTER_SIZE", "8")
@@ -289,7 +290,7 @@ def test_launch_plan_rules(monkeypatch):
     monkeypatch.delenv("BIC_CLUSTER_SIZE")
     assert nat.plan_slices(N, 20, [(8, 49152 * 8)])["cluster"] == 8 and nat.plan_slices(N, 20, [(3, 49153)])["cluster"] == 2
     assert nat.plan_slices(N, 20, [(8, 49152 * 8 + 1)])["cluster"] == 0      # beyond 8 x 192 KB of distributed shared memory
-    monkeypatch.setenv("BIC_CLUSTER", "0")
+    monkeypatch.delenv("BIC_CLUSTER")
     diab = nat.plan_slices(N, 413, fams, tables_in_hbm=True)
     assert diab["ranged"] and diab["passes"] == 4 and diab["cluster"] == 0
     assert diab["slices"][1] < 20 and diab["slices"][2] < 10 and diab["slices"][3] <= N // (4 * 194481)
@@ -312,7 +313,6 @@ def test_launch_plan_rules(monkeypatch):
     monkeypatch.setenv("BIC_RANGE_PASSES", "0")
     assert not nat.plan_slices(N, 413, fams)["ranged"]
     monkeypatch.delenv("BIC_RANGE_PASSES")
-    monkeypatch.delenv("BIC_CLUSTER")
 
     # argument checks
     bad = nat.PlanIn(sm_count=0, N=10, n=2)
