@@ -716,8 +716,8 @@ def main():
     kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory, lane replicas for the small ones)",
                "k_count<512,false> (tables <= 12288 cells in shared memory)",
                "k_count<1024,false> (tables <= 49152 cells in shared memory, one CTA per SM)",
-               "k_count_cluster<1024> (tables > 49152 cells in the distributed shared memory of a thread-block cluster; "
-               "k_count<256,true> L2 atomics when rows are few)"]
+               "k_count<1024,false,true> (tables > 49152 cells: shared-memory sub-range passes; k_count<256,true> L2 atomics "
+               "when rows are few; k_count_cluster with BIC_CLUSTER=1)"]
     dom = int(np.argmax(prof["class_ms"]))
     dom_ms, dom_launches = prof["class_ms"][dom], max(prof["class_launches"][dom], 1)
     achieved = prof["class_alg_bytes"][dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
