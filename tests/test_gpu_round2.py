@@ -395,3 +395,50 @@ def test_tma_staged_tiles_match_default_path(N, monkeypatch):
         for (i, ps), t in zip(fams, tabs):
             assert np.array_equal(t, O.family_counts(codes, card, i, ps)), (N, i, ps)
         assert np.array_equal(s.score_families_csr(node, off, par, no_cache=True), want)
+
+
+# --------------------------------------------- cache checkpoints: content tag, key validation
+def test_cache_checkpoint_refuses_other_content_and_bad_keys(sachs, tmp_path):
+    """ADVICE (low): a checkpoint is tied to the dataset's CONTENT (device-side fingerprint), not only
+    its shape, and to iss for bde terms; bic_cache_import validates parent masks and duplicates."""
+    codes, card = sachs
+    dags = synth.er_candidates(11, 200, 8, 25, 5, seed=2)
+    path = str(tmp_path / "cache.npz")
+    with pkg.BicScorer(codes, card) as s:
+        want = s.score_adjacency(dags)
+        assert s.save_cache(path) > 0
+    other = codes.copy()
+    other[3, 17] = (other[3, 17] + 1) % 3                     # same shape and cardinalities, one state differs
+    with pkg.BicScorer(other, card) as s:
+        with pytest.raises(ValueError):
+            s.load_cache(path)
+    with pkg.BicScorer(np.ascontiguousarray(codes[:, ::-1]), card) as s:      # the same rows in another order: another dataset
+        with pytest.raises(ValueError):
+            s.load_cache(path)
+    with pkg.BicScorer(codes, card) as s:
+        assert s.load_cache(path) > 0
+        s.profile_reset()
+        assert np.array_equal(s.score_adjacency(dags), want)
+        assert s.profile()["families_counted"] == 0           # everything came from the checkpoint
+    # bde terms depend on iss
+    with pkg.BicScorer(codes, card, metric="bde", iss=2.0) as s:
+        s.score_adjacency(dags[:20])
+        s.save_cache(path)
+    with pkg.BicScorer(codes, card, metric="bde", iss=3.0) as s:
+        with pytest.raises(ValueError):
+            s.load_cache(path)
+    # raw import: bad parent bit, self parent, duplicate key
+    with pkg.BicScorer(codes, card) as s:
+        lib = nat.lib()
+        terms, nparams = np.zeros(2), np.zeros(2)
+        for keys in ([[0, 1 << 11], [1, 0]],        # parent index 11 >= n
+                     [[2, 1 << 2], [1, 0]],         # node 2 as its own parent
+                     [[11, 0], [1, 0]],             # node 11 >= n
+                     [[3, 0b110000], [3, 0b110000]]):   # the same family twice
+            k = np.array(keys, dtype=np.uint64)
+            rc = lib.bic_cache_import(s._ctx, k.ctypes.data, terms.ctypes.data, nparams.ctypes.data, 2, 0)
+            assert rc == -2, keys
+            assert s.cache_stats()["families"] == 0
+        k = np.array([[3, 0b110000], [4, 0b1]], dtype=np.uint64)
+        assert lib.bic_cache_import(s._ctx, k.ctypes.data, terms.ctypes.data, nparams.ctypes.data, 2, 0) == 0
+        assert s.cache_stats()["families"] == 2
