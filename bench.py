@@ -380,19 +380,28 @@ def main():
     total_steps = args.warmup + args.steps
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # L2 flush between steps (126 MB L2)
 
-    def time_steps(step_fn, first, count, profile_of=None):
-        """`count` steps starting at batch index `first`, L2 flushed before each; CUDA events on torch's
-        stream bracket the (synchronous) calls; max over ranks.  Returns (ms, profile, clocks)."""
+    def time_steps(step_fn, first, count, profile_of=None, warm=0):
+        """`warm` untimed steps (batches 0 .. warm-1), then `count` timed steps starting at batch index
+        `first`, L2 flushed before each; CUDA events on torch's stream bracket the (synchronous) calls;
+        max over ranks.  The clock sampler (an nvidia-smi child) is started before the warm-up so that
+        its start-up does not fall into a timed region of a few milliseconds.  Returns (ms, profile, clocks)."""
+        sampler = ClockSampler(local_rank) if (rank == 0 and profile_of is not None) else None
+        for s in range(warm):
+            flush_buf.zero_()
+            step_fn(s)
+        if sampler is not None and warm == 0:
+            time.sleep(0.3)
         if profile_of is not None:
             profile_of.profile_enable(True)
             profile_of.profile_reset()
-        sampler = ClockSampler(local_rank) if (rank == 0 and profile_of is not None) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for s in range(first, first + count):
             flush_buf.zero_()
+            t_host = time.perf_counter()
             step_fn(s)
+            dbg(step_fn.__name__, "step", s, "%.3f ms host" % (1e3 * (time.perf_counter() - t_host)))
         e1.record()
         barrier()
         ms = allmax(e0.elapsed_time(e1))
@@ -458,15 +467,11 @@ def main():
             scorer.cache_clear()
             return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False, extra_flags=local_flag)
 
-    for s in range(args.warmup):
-        step_resident(s)
-    ms_res, prof, clocks = time_steps(step_resident, args.warmup, args.steps, profile_of=scorer)
+    ms_res, prof, clocks = time_steps(step_resident, args.warmup, args.steps, profile_of=scorer, warm=args.warmup)
     checksum = float(dev_out.sum().item())
     last_scores = dev_out.clone()
     count_ms_ranks = allgather_floats(prof["count_ms"] / args.steps)
-    for s in range(args.warmup):
-        step_e2e(s)
-    ms_e2e, prof_e2e, _ = time_steps(step_e2e, args.warmup, args.steps, profile_of=scorer)
+    ms_e2e, prof_e2e, _ = time_steps(step_e2e, args.warmup, args.steps, profile_of=scorer, warm=args.warmup)
     assert not np.isnan(host_out.numpy()).any()
     e2e_matches_resident = bool(np.array_equal(host_out.numpy(), last_scores.cpu().numpy()))
 
@@ -556,8 +561,7 @@ def main():
         def step_alone(s):
             plain.cache_clear()
             return plain.score_adjacency_into(dev_adj[s].data_ptr(), batch, dev_out.data_ptr(), device=True)
-        step_alone(0)
-        ms_alone, prof_alone, _ = time_steps(step_alone, args.warmup, min(3, args.steps), profile_of=plain)
+        ms_alone, prof_alone, _ = time_steps(step_alone, args.warmup, min(3, args.steps), profile_of=plain, warm=1)
         # (c) one GPU on the SAME global batch (N x batch DAGs): the like-for-like 1-GPU rate
         glob = torch.empty((world * batch, n, n), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(glob, dev_adj[args.warmup].contiguous())
@@ -625,9 +629,7 @@ def main():
             def rstep_e2e(s, rs=rs):
                 rs.cache_clear()
                 return rs.score_csr_into(csr_h[s][0].data_ptr(), csr_h[s][1].data_ptr(), rbatch, r_host_out.data_ptr(), device=False)
-            for s in range(rwarm):
-                rstep(s)
-            ms_r, pr, _ = time_steps(rstep, rwarm, rsteps, profile_of=rs)
+            ms_r, pr, _ = time_steps(rstep, rwarm, rsteps, profile_of=rs, warm=rwarm)
             res = {"ms_per_step": ms_r / rsteps, "dags_per_s": rbatch * rsteps / (ms_r * 1e-3),
                    "count_ms_per_step": pr["count_ms"] / rsteps, "exchange_ms_per_step": pr["exchange_ms"] / rsteps,
                    "exchange_bytes_per_step": pr["exchange_bytes"] / rsteps, "kernel_launches_per_step": pr["kernel_launches"] / rsteps,
@@ -635,7 +637,7 @@ def main():
                    "families_counted_per_step": pr["families_counted"] / rsteps, "families_derived_per_step": pr["families_derived"] / rsteps,
                    "family_count_rows_per_sec_per_gpu": pr["rows_counted"] / (pr["count_ms"] * 1e-3) if pr["count_ms"] > 0 else None}
             if mode == "fused":
-                ms_re, _, _ = time_steps(rstep_e2e, rwarm, rsteps)
+                ms_re, _, _ = time_steps(rstep_e2e, rwarm, rsteps, warm=1)
                 res["e2e_ms_per_step"] = ms_re / rsteps
                 results["bits"] = r_out.clone()
                 # counts of one family per count-kernel class against the C oracle on the gathered columns (rank 0)

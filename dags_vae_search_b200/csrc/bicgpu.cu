@@ -135,6 +135,7 @@ struct bic_ctx {
         int class0_threads = 256;              // BIC_CLASS0_THREADS: 256, 512 or 1024
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
                                                //   are counted in passes (0: always straight into HBM with L2 atomics)
+        int class1_threads = 512;              // BIC_CLASS1_THREADS: 256, 512 or 1024 (48 KB tables)
         int class2_threads = 1024;             // BIC_CLASS2_THREADS: 512 or 1024 (classes 2 and 3-in-passes: one CTA per SM)
         int p2_vec = 4;                        // BIC_P2_VEC: 32-bit words of a packed column per thread-iteration (4, 2 or 1)
         int cluster = 0;                       // BIC_CLUSTER=1: class 3 in one pass over a thread-block cluster (measured 3x slower than sub-range passes)
@@ -155,6 +156,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_L2_WINDOW_MAX_MB")) { long long mb = atoll(e); if (mb > 0) l2_window_max = mb << 20; }
             if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 49152) { class0_words = (u32)w; class0_words_packed = (u32)w; } }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
+            if (const char *e = getenv("BIC_CLASS1_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) class1_threads = t; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
             if (const char *e = getenv("BIC_P2_VEC")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) p2_vec = v; }
             if (const char *e = getenv("BIC_CLUSTER")) cluster = atoi(e) != 0;
@@ -657,7 +659,10 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32) + ring256)));
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32) + ring512)));
         if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));
-        if (k == 1) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32) + ring512)));
+        const int c1t = c->tune.class1_threads;
+        if (k == 1 && c1t == 256) TRY((launch_count<256, false>(c, a, items, cap[1] * sizeof(u32) + ring256)));
+        if (k == 1 && c1t == 512) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32) + ring512)));
+        if (k == 1 && c1t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[1] * sizeof(u32))));
         const bool wide = c->tune.class2_threads == 1024;
         if (k == 2 && !wide) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 2 && wide) TRY((launch_count<1024, false>(c, a, items, cap[2] * sizeof(u32))));
