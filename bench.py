@@ -379,15 +379,21 @@ def main():
     famshard = (not sharded) and world > 1 and args.multi == "family"
     total_steps = args.warmup + args.steps
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # L2 flush between steps (126 MB L2)
+    # Timing rule: flush L2 between timed steps OR use inputs larger than L2.  Datasets of a gigabyte and
+    # more (diabetes- / pigs-shaped: 5.2 / 5.5 GB, every step streams hundreds of their columns) are the
+    # latter; the others are flushed.
+    big_input = lambda r, nn: r * nn >= (1 << 30)
+    flush_main = not big_input(rows, cfg["n"])
 
-    def time_steps(step_fn, first, count, profile_of=None, warm=0):
+    def time_steps(step_fn, first, count, profile_of=None, warm=0, flush=True):
         """`warm` untimed steps (batches 0 .. warm-1), then `count` timed steps starting at batch index
         `first`, L2 flushed before each; CUDA events on torch's stream bracket the (synchronous) calls;
         max over ranks.  The clock sampler (an nvidia-smi child) is started before the warm-up so that
         its start-up does not fall into a timed region of a few milliseconds.  Returns (ms, profile, clocks)."""
         sampler = ClockSampler(local_rank) if (rank == 0 and profile_of is not None) else None
         for s in range(warm):
-            flush_buf.zero_()
+            if flush:
+                flush_buf.zero_()
             step_fn(s)
         if sampler is not None and warm == 0:
             time.sleep(0.3)
@@ -398,7 +404,8 @@ def main():
         barrier()
         e0.record()
         for s in range(first, first + count):
-            flush_buf.zero_()
+            if flush:
+                flush_buf.zero_()
             t_host = time.perf_counter()
             step_fn(s)
             dbg(step_fn.__name__, "step", s, "%.3f ms host" % (1e3 * (time.perf_counter() - t_host)))
@@ -467,11 +474,11 @@ def main():
             scorer.cache_clear()
             return scorer.score_adjacency_into(host_adj[s].data_ptr(), batch, host_out.data_ptr(), device=False, extra_flags=local_flag)
 
-    ms_res, prof, clocks = time_steps(step_resident, args.warmup, args.steps, profile_of=scorer, warm=args.warmup)
+    ms_res, prof, clocks = time_steps(step_resident, args.warmup, args.steps, profile_of=scorer, warm=args.warmup, flush=flush_main)
     checksum = float(dev_out.sum().item())
     last_scores = dev_out.clone()
     count_ms_ranks = allgather_floats(prof["count_ms"] / args.steps)
-    ms_e2e, prof_e2e, _ = time_steps(step_e2e, args.warmup, args.steps, profile_of=scorer, warm=args.warmup)
+    ms_e2e, prof_e2e, _ = time_steps(step_e2e, args.warmup, args.steps, profile_of=scorer, warm=args.warmup, flush=flush_main)
     assert not np.isnan(host_out.numpy()).any()
     e2e_matches_resident = bool(np.array_equal(host_out.numpy(), last_scores.cpu().numpy()))
 
@@ -629,7 +636,7 @@ def main():
             def rstep_e2e(s, rs=rs):
                 rs.cache_clear()
                 return rs.score_csr_into(csr_h[s][0].data_ptr(), csr_h[s][1].data_ptr(), rbatch, r_host_out.data_ptr(), device=False)
-            ms_r, pr, _ = time_steps(rstep, rwarm, rsteps, profile_of=rs, warm=rwarm)
+            ms_r, pr, _ = time_steps(rstep, rwarm, rsteps, profile_of=rs, warm=rwarm, flush=False)
             res = {"ms_per_step": ms_r / rsteps, "dags_per_s": rbatch * rsteps / (ms_r * 1e-3),
                    "count_ms_per_step": pr["count_ms"] / rsteps, "exchange_ms_per_step": pr["exchange_ms"] / rsteps,
                    "exchange_bytes_per_step": pr["exchange_bytes"] / rsteps, "kernel_launches_per_step": pr["kernel_launches"] / rsteps,
@@ -637,7 +644,7 @@ def main():
                    "families_counted_per_step": pr["families_counted"] / rsteps, "families_derived_per_step": pr["families_derived"] / rsteps,
                    "family_count_rows_per_sec_per_gpu": pr["rows_counted"] / (pr["count_ms"] * 1e-3) if pr["count_ms"] > 0 else None}
             if mode == "fused":
-                ms_re, _, _ = time_steps(rstep_e2e, rwarm, rsteps, warm=1)
+                ms_re, _, _ = time_steps(rstep_e2e, rwarm, rsteps, warm=1, flush=False)
                 res["e2e_ms_per_step"] = ms_re / rsteps
                 results["bits"] = r_out.clone()
                 # counts of one family per count-kernel class against the C oracle on the gathered columns (rank 0)
@@ -687,6 +694,7 @@ def main():
         results.pop("bits")
         row_leg = {"workload": rcfg["desc"], "rows_per_gpu": rrows, "rows_total": rrows * world, "n": rn, "dags_per_step": rbatch,
                    "steps": rsteps, "warmup": rwarm, "cache": "cleared at the start of every step (cold)",
+                   "l2": f"no flush: input larger than L2 (dataset {rrows * rn / 1e9:.1f} GB uint8 per GPU)",
                    "fused_reduce_scatter": results["fused"], "nccl_allreduce": results["nccl"],
                    "one_gpu_own_shard": results["one_gpu"],
                    "step_ratio_vs_one_gpu_shard": results["fused"]["ms_per_step"] / results["one_gpu"]["ms_per_step"],
@@ -735,8 +743,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts + f64 reduce", "data": "synthetic",
         "config": workload_config(cfg, rows, batch, {
             "cache": "family-score cache cleared at the start of every step (cold)",
-            "l2": (f"L2 flushed before every timed step (256 MB written inside the timed region); dataset {rows * n / 1e6:.0f} MB uint8"
-                   + (f" + {rows * n / 4e6:.0f} MB 2-bit packed copy, re-read by every streamed family within a step" if rows >= (1 << 20) else "")),
+            "l2": ((f"L2 flushed before every timed step (256 MB written inside the timed region); dataset {rows * n / 1e6:.0f} MB uint8"
+                    + (f" + {rows * n / 4e6:.0f} MB 2-bit packed copy, re-read by every streamed family within a step" if rows >= (1 << 20) else ""))
+                   if flush_main else f"no flush: input larger than L2 (dataset {rows * n / 1e9:.1f} GB uint8, streamed by every step; L2 126 MB)"),
             "parallelism": (f"row-sharded x{world} ({rows} rows per GPU, {rows * world} in total), count tables summed by the reduce-scatter fused into the count kernels"
                             if sharded else (f"candidate-sharded x{world}, dataset replicated; every rank passes its own {batch} DAGs, the library "
                                              f"all-gathers the family keys over NVLink into one global batch ({batch * world} DAGs) that every rank "

@@ -141,6 +141,9 @@ struct bic_ctx {
         int cluster = 0;                       // BIC_CLUSTER=1: class 3 in one pass over a thread-block cluster (measured 3x slower than sub-range passes)
         int cluster_size = 0;                  // BIC_CLUSTER_SIZE: force 2, 4 or 8 CTAs per cluster (0: smallest that holds the table)
         int cluster_threads = 1024;            // BIC_CLUSTER_THREADS: 512 or 1024
+        bool park_cells = true;                // BIC_NO_CELLS=1: class-3 passes recompute the cell index of every row instead of reading it
+                                               //   from the scratch k_cells fills once (round-1 behaviour)
+        long long cells_max_mb = 4096;         // BIC_CELLS_MAX_MB: scratch limit; above it the passes recompute
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
                                                //   fused reduce-scatter over peer memory
@@ -163,6 +166,8 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER_SIZE")) { int v = atoi(e); if (v == 0 || v == 2 || v == 4 || v == 8) cluster_size = v; }
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
+            if (const char *e = getenv("BIC_NO_CELLS")) park_cells = atoi(e) == 0;
+            if (const char *e = getenv("BIC_CELLS_MAX_MB")) { long long v = atoll(e); if (v >= 0) cells_max_mb = v; }
             if (const char *e = getenv("BIC_NO_PUSH")) push = atoi(e) == 0;
             if (const char *e = getenv("BIC_PUSH_WORLD1")) push_world1 = atoi(e) != 0;
             if (const char *e = getenv("BIC_XCHG_MB")) { long long v = atoll(e); if (v > 0 && v <= 4096) xchg_mb = v; }
@@ -192,7 +197,7 @@ struct bic_ctx {
     u32 **d_peer = nullptr;              // device array [world] of exchange-buffer pointers (own buffer at [rank])
     int xchg_state = 0;                  // 0 not tried, 1 ready, -1 unavailable (fall back to ncclAllReduce of the tables)
     int *d_barrier = nullptr;            // 4 bytes all-reduced as the "all pushes have landed" barrier
-    DevBuf terms, gkeys, gbad;           // staged family terms (one all-reduce), all-gathered keys / reject flags
+    DevBuf terms, gkeys, gbad, cellbuf;  // staged family terms (one all-reduce), all-gathered keys / reject flags, parked cell indices (class 3)
     cudaEvent_t ev_wait = nullptr;       // bic_wait_stream
     bool fast_ok = true;     // small warm batches: try k_score_small first (off after a miss, on again after an all-hit call)
 };
@@ -654,6 +659,18 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         a.cap_words = cap[k];
         const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
         const u32 clwords = clustered ? (u32)((max_cells + CL - 1) / CL) : 0;
+        a.cellbuf = nullptr;
+        if (k == 3 && ranged && c->tune.park_cells && cnt <= 65535) {   // compute every row's cell once, the passes only compare and increment
+            const size_t bytes = (size_t)cnt * (size_t)c->stride * sizeof(u32);
+            if (bytes <= ((size_t)c->tune.cells_max_mb << 20)) {
+                CU(c->cellbuf.ensure(bytes));
+                a.cellbuf = c->cellbuf.as<u32>();
+                const long long nvec = (c->N + 15) >> 4;
+                dim3 grid((unsigned)std::min<long long>((nvec + 255) / 256, std::max<long long>(1, (long long)c->sm_count * 8 / cnt)), (unsigned)cnt);
+                k_cells<<<grid, 256, 0, c->stream>>>(a); LAUNCH(c);
+                CU(cudaGetLastError());
+            }
+        }
         a.stage_words = k == 3 ? (clustered ? clwords : ranged ? span : GLOBAL_STAGE) : cap[k];
         const size_t ring256 = a.tma ? tma_ring_bytes(256) : 0, ring512 = a.tma ? tma_ring_bytes(512) : 0;   // TMA staging ring behind the table
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32) + ring256)));
@@ -1094,7 +1111,7 @@ int bic_destroy(bic_ctx *c) {
     DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
                       &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
                       &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_best,
-                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad};
+                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad, &c->cellbuf};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
     if (c->data2) cudaFree(c->data2);

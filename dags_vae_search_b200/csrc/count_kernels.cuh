@@ -41,6 +41,7 @@ struct CountArgs {
     double *np_out;          // (r - 1) * q
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
+    u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
     int p2_vec;              // packed path: 32-bit words of a column one thread loads per iteration (4, 2 or 1)
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
@@ -717,6 +718,89 @@ __device__ __forceinline__ void push_table(const CountArgs &a, int j, const u32 
     }
 }
 
+// Class 3 in sub-range passes, step 1: the cell index of every row is computed ONCE (k_cells) and
+// parked in HBM scratch, 4 bytes per row; the P passes of k_count<.., false, true> then read it back
+// (from L2: the passes of a slice are neighbours in the grid) and only compare and increment.  The
+// round-1 passes recomputed the mixed-radix index of every row in each pass and threw (P - 1) / P of
+// them away (ncu: issue-active 76 %, 0.15 of the HBM peak).
+template <int K>
+__device__ __forceinline__ void cells_rows_k(const FamMeta &m, const uint8_t *__restrict__ data, long long stride, long long v,
+                                             u32 *out) {
+    uint4 w[K + 1];
+    u32 rad[K + 1];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        w[a] = ld_stream_v4(data + (long long)m.par[a] * stride + v * 16);
+        rad[a] = m.rad[a];
+    }
+    w[K] = ld_stream_v4(data + (long long)m.node * stride + v * 16);
+    rad[K] = (u32)m.r;
+    u32 cell[16];
+    cells_u32<K>(w, rad, 1u, cell);
+    uint4 *o = reinterpret_cast<uint4 *>(out + v * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_uint4(cell[4 * i], cell[4 * i + 1], cell[4 * i + 2], cell[4 * i + 3]);
+}
+
+// grid = (CTAs per family, class-3 families); every thread turns 16 rows per iteration into 16 cells
+__global__ void __launch_bounds__(256) k_cells(CountArgs a) {
+    __shared__ FamMeta m;
+    const int jj = blockIdx.y;
+    const int j = a.jobs[jj];
+    if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
+    __syncthreads();
+    u32 *out = a.cellbuf + (size_t)jj * (size_t)a.stride;
+    const long long nvec = (a.N + 15) >> 4;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+        switch (m.k) {
+            case 0: cells_rows_k<0>(m, a.data, a.stride, v, out); break;
+            case 1: cells_rows_k<1>(m, a.data, a.stride, v, out); break;
+            case 2: cells_rows_k<2>(m, a.data, a.stride, v, out); break;
+            case 3: cells_rows_k<3>(m, a.data, a.stride, v, out); break;
+            case 4: cells_rows_k<4>(m, a.data, a.stride, v, out); break;
+            case 5: cells_rows_k<5>(m, a.data, a.stride, v, out); break;
+            case 6: cells_rows_k<6>(m, a.data, a.stride, v, out); break;
+            default: {   // k > 6: columns one at a time
+                u32 cell[16];
+#pragma unroll
+                for (int b = 0; b < 16; ++b) cell[b] = 0;
+                for (int x = 0; x <= m.k; ++x) {
+                    const uint4 w = ld_stream_v4(a.data + (long long)(x < m.k ? m.par[x] : m.node) * a.stride + v * 16);
+                    const u32 rad = x < m.k ? m.rad[x] : (u32)m.r;
+                    const u32 ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) cell[i * 4 + b] = cell[i * 4 + b] * rad + ((ws[i] >> (8 * b)) & 0xffu);
+                }
+                uint4 *o = reinterpret_cast<uint4 *>(out + v * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = make_uint4(cell[4 * i], cell[4 * i + 1], cell[4 * i + 2], cell[4 * i + 3]);
+            }
+        }
+    }
+}
+
+// step 2 of a pass: 16 parked cells per thread-iteration; the CTA owns the cells [lo, lo + span)
+template <int THREADS>
+__device__ __forceinline__ void count_rows_cells(const u32 *__restrict__ cells, long long N, long long v0, long long v1, u32 *hist,
+                                                 u32 lo, u32 span) {
+    for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(cells + v * 16);
+        uint4 c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = __ldcg(p + i);
+        const u32 cs[16] = {c[0].x, c[0].y, c[0].z, c[0].w, c[1].x, c[1].y, c[1].z, c[1].w,
+                            c[2].x, c[2].y, c[2].z, c[2].w, c[3].x, c[3].y, c[3].z, c[3].w};
+        const int nv = v * 16 + 16 <= N ? 16 : (int)(N - v * 16);
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const u32 d = cs[b] - lo;
+            if (b < nv && d < span) bump_off<false>(hist, d << 2);
+        }
+    }
+}
+
 // RANGE (class 3 when the rows dwarf the table): the table does not fit one CTA's shared memory,
 // so a (family, slice) is counted in P passes; pass p keeps cells [p * span, (p + 1) * span) in
 // shared memory, streams the slice and skips the rows whose cell lies elsewhere.  The passes of a
@@ -785,6 +869,8 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
         if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist);
         else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist);
         else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+    } else if (RANGE && a.cellbuf) {
+        count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
     } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.tma && m.k <= 6) {
         uint8_t *ring = reinterpret_cast<uint8_t *>(s_hist + a.cap_words);
         switch (m.k) {
