@@ -55,7 +55,7 @@ class CacheStats(ctypes.Structure):
 class PlanIn(ctypes.Structure):
     _fields_ = [("sm_count", ctypes.c_int32), ("N", ctypes.c_int64), ("n", ctypes.c_int32), ("max_cells", ctypes.c_int64),
                 ("tables_in_hbm", ctypes.c_int32), ("class_count", ctypes.c_int64 * 4), ("class_cells", ctypes.c_int64 * 4),
-                ("class_alg_bytes", ctypes.c_int64 * 4)]
+                ("class_alg_bytes", ctypes.c_int64 * 4), ("all_packed", ctypes.c_int32)]
 
 
 class PlanOut(ctypes.Structure):
@@ -63,11 +63,11 @@ class PlanOut(ctypes.Structure):
                 ("cluster", ctypes.c_int32)]
 
 
-def plan_slices(N: int, n: int, families, sm_count: int = 148, tables_in_hbm: bool = False) -> dict:
+def plan_slices(N: int, n: int, families, sm_count: int = 148, tables_in_hbm: bool = False, all_packed: bool = False) -> dict:
     """The launch plan the library would use for one batch of new families (host arithmetic only,
     works without a GPU).  ``families`` = iterable of (k, cells): number of parents and q*r."""
     bounds = (2048, 12288, 49152)
-    pin = PlanIn(sm_count=sm_count, N=N, n=n, max_cells=0, tables_in_hbm=int(tables_in_hbm))
+    pin = PlanIn(sm_count=sm_count, N=N, n=n, max_cells=0, tables_in_hbm=int(tables_in_hbm), all_packed=int(all_packed))
     for k, cells in families:
         cls = sum(cells > b for b in bounds)
         pin.class_count[cls] += 1

@@ -141,8 +141,8 @@ struct bic_ctx {
         int cluster = 0;                       // BIC_CLUSTER=1: class 3 in one pass over a thread-block cluster (measured 3x slower than sub-range passes)
         int cluster_size = 0;                  // BIC_CLUSTER_SIZE: force 2, 4 or 8 CTAs per cluster (0: smallest that holds the table)
         int cluster_threads = 1024;            // BIC_CLUSTER_THREADS: 512 or 1024
-        bool park_cells = true;                // BIC_NO_CELLS=1: class-3 passes recompute the cell index of every row instead of reading it
-                                               //   from the scratch k_cells fills once (round-1 behaviour)
+        bool park_cells = false;               // BIC_PARK_CELLS=1: class-3 passes read the cell index of every row from scratch that k_cells
+                                               //   fills once, instead of recomputing it per pass (measured slower: 0.57 vs 0.38 ms)
         long long cells_max_mb = 4096;         // BIC_CELLS_MAX_MB: scratch limit; above it the passes recompute
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
@@ -166,7 +166,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER_SIZE")) { int v = atoi(e); if (v == 0 || v == 2 || v == 4 || v == 8) cluster_size = v; }
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
-            if (const char *e = getenv("BIC_NO_CELLS")) park_cells = atoi(e) == 0;
+            if (const char *e = getenv("BIC_PARK_CELLS")) park_cells = atoi(e) != 0;
             if (const char *e = getenv("BIC_CELLS_MAX_MB")) { long long v = atoll(e); if (v >= 0) cells_max_mb = v; }
             if (const char *e = getenv("BIC_NO_PUSH")) push = atoi(e) == 0;
             if (const char *e = getenv("BIC_PUSH_WORLD1")) push_world1 = atoi(e) != 0;
@@ -430,8 +430,11 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
             // the number of rounds a slice takes: 128 MB / rounds.
             // Taken only when the HBM traffic it saves (the class's algorithmic row bytes beyond
             // one pass over the dataset) outweighs the extra merges.
+            // all-packed datasets stream a quarter of the bytes per row: the same L2 footprint is 4x the rows
+            // (measured on the alarm-shaped step: 58.2 / 57.1 / 56.8 / 56.9 ms with 32 / 64 / 128 / 400 MB)
+            const long long wmin = tune.l2_window * (in.all_packed ? 4 : 1);
             const long long win = !tune.slice_model ? tune.l2_window :
-                ctas <= slots ? tune.l2_window_max : std::max(tune.l2_window, tune.l2_window_max / 2 * slots / ctas);
+                ctas <= slots ? std::max(wmin, tune.l2_window_max) : std::max(wmin, tune.l2_window_max / 2 * slots / ctas);
             const long long s_l2 = ((long long)in.n * in.N + win - 1) / win;
             if (s_l2 > S && !rng3) {
                 const double row_bytes = (double)in.class_alg_bytes[k] - 4.0 * (double)in.class_cells[k];
@@ -571,7 +574,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     NeedArgs na;
     na.all = all_tables ? 1 : 0;
     bic_plan_in_t pin;
-    pin.sm_count = c->sm_count; pin.N = c->N; pin.n = c->n; pin.max_cells = h.max_cells; pin.tables_in_hbm = all_tables ? 1 : 0;
+    pin.sm_count = c->sm_count; pin.N = c->N; pin.n = c->n; pin.max_cells = h.max_cells; pin.tables_in_hbm = all_tables ? 1 : 0; pin.all_packed = c->all_packed ? 1 : 0;
     for (int k = 0; k < NCLASS; ++k) {
         pin.class_count[k] = h.class_count[k];
         pin.class_cells[k] = (long long)h.class_cells[k];

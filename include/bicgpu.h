@@ -215,6 +215,8 @@ typedef struct {
     int64_t class_count[4];    /* families per class (<= 2048 / 12288 / 49152 cells / larger)   */
     int64_t class_cells[4];    /* sum of q*r per class                                          */
     int64_t class_alg_bytes[4];/* sum of (k+1)*N + 4*q*r per class                              */
+    int32_t all_packed;        /* 1: every column also has a 2-bit packed copy that the families *
+                                * stream instead (a quarter of the bytes per row)               */
 } bic_plan_in_t;
 typedef struct {
     int32_t slices[4];         /* row slices per family, per class                              */

@@ -471,13 +471,13 @@ def test_class3_cluster_passes_and_l2_atomics_match_oracle(monkeypatch):
         assert_scores(scores, want_scores)
         return scores
 
-    ranged = run()                                            # sub-range passes on parked cell indices (k_cells)
-    monkeypatch.setenv("BIC_NO_CELLS", "1")
-    assert np.array_equal(run(), ranged)                      # passes that recompute the index (round 1)
-    monkeypatch.delenv("BIC_NO_CELLS")
+    ranged = run()                                            # sub-range passes
+    monkeypatch.setenv("BIC_PARK_CELLS", "1")
+    assert np.array_equal(run(), ranged)                      # passes on cell indices parked once by k_cells
     monkeypatch.setenv("BIC_CELLS_MAX_MB", "1")
     assert np.array_equal(run(), ranged)                      # scratch limit exceeded: recompute
     monkeypatch.delenv("BIC_CELLS_MAX_MB")
+    monkeypatch.delenv("BIC_PARK_CELLS")
     monkeypatch.setenv("BIC_CLUSTER", "1")
     assert np.array_equal(run(), ranged)                      # thread-block clusters
     monkeypatch.setenv("BIC_CLUSTER_THREADS", "512")

@@ -272,6 +272,9 @@ def test_launch_plan_rules(monkeypatch):
     N = 10_000_000
     alarm = nat.plan_slices(N, 37, [(5, 700)] * 17500 + [(6, 4000)] * 1800 + [(6, 16384)])
     assert alarm["slices"][0] == windows(37, N, 32) and not alarm["ranged"] and alarm["passes"] == 1
+    # the same step when every column streams from the 2-bit packed copy: 4x the rows per window
+    packed = nat.plan_slices(N, 37, [(5, 700)] * 17500 + [(6, 4000)] * 1800 + [(6, 16384)], all_packed=True)
+    assert packed["slices"][0] == windows(37, N, 128)
     assert all(1 <= s <= N // 65536 for s in alarm["slices"])
     # a handful of families of a search step: enough slices to occupy the GPU, well below the window count of a full pass
     few = nat.plan_slices(N, 37, [(5, 700)] * 40)
