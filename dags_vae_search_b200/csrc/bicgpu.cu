@@ -144,6 +144,7 @@ struct bic_ctx {
         bool park_cells = false;               // BIC_PARK_CELLS=1: class-3 passes read the cell index of every row from scratch that k_cells
                                                //   fills once, instead of recomputing it per pass (measured slower: 0.57 vs 0.38 ms)
         long long cells_max_mb = 4096;         // BIC_CELLS_MAX_MB: scratch limit; above it the passes recompute
+        bool dyn = false;                      // BIC_DYN=1: packed path, warps draw row chunks from a ticket instead of a fixed stride
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
                                                //   fused reduce-scatter over peer memory
@@ -166,6 +167,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER_SIZE")) { int v = atoi(e); if (v == 0 || v == 2 || v == 4 || v == 8) cluster_size = v; }
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
+            if (const char *e = getenv("BIC_DYN")) dyn = atoi(e) != 0;
             if (const char *e = getenv("BIC_PARK_CELLS")) park_cells = atoi(e) != 0;
             if (const char *e = getenv("BIC_CELLS_MAX_MB")) { long long v = atoll(e); if (v >= 0) cells_max_mb = v; }
             if (const char *e = getenv("BIC_NO_PUSH")) push = atoi(e) == 0;
@@ -620,6 +622,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.bd_mode = c->cache_mode;
     a.p2_vec = c->tune.p2_vec;
     a.tma = c->tune.tma ? 1 : 0;
+    a.dyn = c->tune.dyn ? 1 : 0;
     a.iss = c->iss;
     a.push = push ? 1 : 0;
     a.rank = c->rank_id; a.world = c->world;

@@ -43,6 +43,7 @@ struct CountArgs {
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
+    int dyn;                 // packed path: warps draw their row chunks from a shared-memory ticket (dynamic) instead of a fixed stride
     int p2_vec;              // packed path: 32-bit words of a column one thread loads per iteration (4, 2 or 1)
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
     double iss;
@@ -468,9 +469,12 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
 }
 
 // [b0, b1): the CTA's slice in 512-row blocks (128 bytes of a packed column)
+// next != NULL: the warps of the CTA draw 32-group chunks from a shared-memory ticket instead of a
+// fixed stride, so that no warp idles at the barrier behind the row loop while another still has
+// iterations left (the ticket of the following chunk is drawn before the current one is processed).
 template <int K, int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                              long long N, long long b0, long long b1, u32 *hist) {
+                                              long long N, long long b0, long long b1, u32 *hist, u32 *next) {
     constexpr int C = K + 1;
     constexpr int C1 = C > 4 ? C - 4 : 0;
     constexpr int ROWS = 16 * VEC;            // rows of one thread-iteration
@@ -488,27 +492,48 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
     for (int a = C1; a < C; ++a) plow *= rad[a];
     const u32 mul = m.mul, plow_mul = plow * mul;
     const long long g0 = b0 * (512 / ROWS), g1 = min(b1 * (512 / ROWS), (N + ROWS - 1) / ROWS);
-    for (long long g = g0 + threadIdx.x; g < g1; g += THREADS) {
-        u32 w[C][VEC];
+    const bool dyn = next != nullptr;
+    const int lane = threadIdx.x & 31;
+    u32 chunk = 0;
+    if (dyn) {
+        if (lane == 0) chunk = atomicAdd(next, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    }
+    long long base = dyn ? g0 + (long long)chunk * 32 : g0 + threadIdx.x;   // dyn: uniform over the warp
+    long long g = dyn ? base + lane : base;
+    while (base < g1) {
+        u32 ahead = 0;
+        if (dyn && lane == 0) ahead = atomicAdd(next, 1u);
+        if (g < g1) {
+            u32 w[C][VEC];
 #pragma unroll
-        for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
-        const long long row0 = g * ROWS;
-        if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS);
-        else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
+            for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
+            const long long row0 = g * ROWS;
+            if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS);
+            else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
+        }
+        if (dyn) {
+            chunk = __shfl_sync(0xffffffffu, ahead, 0);
+            base = g0 + (long long)chunk * 32;
+            g = base + lane;
+        } else {
+            g += THREADS;
+            base = g;
+        }
     }
 }
 
 template <int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2_k(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                                long long N, long long b0, long long b1, u32 *hist) {
+                                                long long N, long long b0, long long b1, u32 *hist, u32 *next) {
     switch (m.k) {
-        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
     }
 }
 
@@ -816,6 +841,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
     __shared__ double s_red[32];
     __shared__ int s_last;
     __shared__ __align__(8) u64 s_full[TMA_STAGES];
+    __shared__ u32 s_next;
 
     // slice-major item order: the CTAs resident at any moment work on the same row window of
     // the dataset, which the host sizes to stay L2-resident
@@ -852,6 +878,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
         m.mul = 4u * R;
         m.lo4 = lo * 4u;
         m.span4 = span * 4u;
+        s_next = 0;
     }
     __syncthreads();
     const u32 R = m.R;
@@ -866,9 +893,10 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
     // depend on the slice, hence no R here: R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
-        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist);
-        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist);
-        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+        u32 *next = a.dyn ? &s_next : nullptr;
+        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist, next);
+        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist, next);
+        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, next);
     } else if (RANGE && a.cellbuf) {
         count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
     } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.tma && m.k <= 6) {
