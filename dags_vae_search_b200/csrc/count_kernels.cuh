@@ -15,6 +15,8 @@
 
 namespace bic {
 
+struct FamMetaC;
+
 struct CountArgs {
     const uint8_t *data;     // [n][stride] uint8 state codes
     const uint8_t *data2;    // [n][stride2] 2-bit packed copy of the columns with <= 4 states (nullable)
@@ -43,7 +45,7 @@ struct CountArgs {
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
-    int dyn;                 // packed path: warps draw their row chunks from a shared-memory ticket (dynamic) instead of a fixed stride
+    const FamMetaC *meta;    // per job: the decoded family (k_decode_jobs), or NULL: thread 0 of every CTA decodes the key
     int p2_vec;              // packed path: 32-bit words of a column one thread loads per iteration (4, 2 or 1)
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
     double iss;
@@ -69,6 +71,19 @@ struct FamMeta {
     int par[KMAX];
     u32 rad[KMAX];
 };
+
+// The decoded family as k_decode_jobs parks it per job (128 bytes): a count CTA fetches it with one
+// coalesced load instead of having thread 0 walk the key and the cardinalities while 255 threads
+// wait at the first barrier (ncu source page, version k: 11 % of all warp samples sat there).
+struct __align__(16) FamMetaC {
+    int k, node, r;
+    u32 q, cells;
+    int small;
+    uint16_t par[KMAX];
+    uint8_t rad[KMAX];
+    u32 pad[2];
+};
+static_assert(sizeof(FamMetaC) == 128, "one 128-byte record per job");
 
 // Thread 0 decodes the key.  Parents ascending, first parent most significant; parents with a
 // single state contribute nothing to the index and are dropped.
@@ -98,6 +113,22 @@ __device__ __forceinline__ void decode_family(const u64 *key, int W64, const int
     m.q = q;
     m.cells = q * (u32)m.r;
     m.small = small;
+}
+
+__global__ void k_decode_jobs(const u64 *__restrict__ keys, long long key_base, int W64, const int *__restrict__ card, long long njobs,
+                              FamMetaC *out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    FamMeta m;
+    decode_family(keys + (key_base + j) * (long long)(W64 + 1), W64, card, m);
+    FamMetaC c;
+    c.k = m.k; c.node = m.node; c.r = m.r; c.q = m.q; c.cells = m.cells; c.small = m.small;
+    for (int a = 0; a < KMAX; ++a) {
+        c.par[a] = a < m.k ? (uint16_t)m.par[a] : 0;
+        c.rad[a] = a < m.k ? (uint8_t)m.rad[a] : 0;
+    }
+    c.pad[0] = c.pad[1] = 0;
+    out[j] = c;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -469,12 +500,9 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
 }
 
 // [b0, b1): the CTA's slice in 512-row blocks (128 bytes of a packed column)
-// next != NULL: the warps of the CTA draw 32-group chunks from a shared-memory ticket instead of a
-// fixed stride, so that no warp idles at the barrier behind the row loop while another still has
-// iterations left (the ticket of the following chunk is drawn before the current one is processed).
 template <int K, int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                              long long N, long long b0, long long b1, u32 *hist, u32 *next) {
+                                              long long N, long long b0, long long b1, u32 *hist) {
     constexpr int C = K + 1;
     constexpr int C1 = C > 4 ? C - 4 : 0;
     constexpr int ROWS = 16 * VEC;            // rows of one thread-iteration
@@ -492,48 +520,30 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
     for (int a = C1; a < C; ++a) plow *= rad[a];
     const u32 mul = m.mul, plow_mul = plow * mul;
     const long long g0 = b0 * (512 / ROWS), g1 = min(b1 * (512 / ROWS), (N + ROWS - 1) / ROWS);
-    const bool dyn = next != nullptr;
-    const int lane = threadIdx.x & 31;
-    u32 chunk = 0;
-    if (dyn) {
-        if (lane == 0) chunk = atomicAdd(next, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    }
-    long long base = dyn ? g0 + (long long)chunk * 32 : g0 + threadIdx.x;   // dyn: uniform over the warp
-    long long g = dyn ? base + lane : base;
-    while (base < g1) {
-        u32 ahead = 0;
-        if (dyn && lane == 0) ahead = atomicAdd(next, 1u);
-        if (g < g1) {
-            u32 w[C][VEC];
+    // (A variant in which the warps draw their row chunks from a shared-memory ticket instead of this
+    // fixed stride, to even out the arrival at the barrier behind the loop, was 3 % slower — and the
+    // loop shape that served both variants cost the fixed stride 7 %: 61.1 vs 56.8 ms per launch.)
+    for (long long g = g0 + threadIdx.x; g < g1; g += THREADS) {
+        u32 w[C][VEC];
 #pragma unroll
-            for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
-            const long long row0 = g * ROWS;
-            if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS);
-            else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
-        }
-        if (dyn) {
-            chunk = __shfl_sync(0xffffffffu, ahead, 0);
-            base = g0 + (long long)chunk * 32;
-            g = base + lane;
-        } else {
-            g += THREADS;
-            base = g;
-        }
+        for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
+        const long long row0 = g * ROWS;
+        if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS);
+        else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
     }
 }
 
 template <int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2_k(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                                long long N, long long b0, long long b1, u32 *hist, u32 *next) {
+                                                long long N, long long b0, long long b1, u32 *hist) {
     switch (m.k) {
-        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
-        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
-        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
-        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
-        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
-        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
-        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, next); break;
+        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
     }
 }
 
@@ -841,7 +851,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
     __shared__ double s_red[32];
     __shared__ int s_last;
     __shared__ __align__(8) u64 s_full[TMA_STAGES];
-    __shared__ u32 s_next;
+    __shared__ FamMetaC s_c;
 
     // slice-major item order: the CTAs resident at any moment work on the same row window of
     // the dataset, which the host sizes to stay L2-resident
@@ -850,10 +860,14 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
     const int in_slice = blockIdx.x - slice * per_slice;
     const int pass = RANGE ? in_slice / a.njobs : 0;
     const int j = a.jobs[in_slice - pass * a.njobs];
-    if (threadIdx.x == 0) decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
+    if (a.meta) {   // one coalesced 128-byte read of the parked record
+        if (threadIdx.x < 8) reinterpret_cast<uint4 *>(&s_c)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.meta + j) + threadIdx.x);
+    } else if (threadIdx.x == 0) {
+        decode_family(a.keys + (a.key_base + j) * (long long)(a.W64 + 1), a.W64, a.card, m);
+    }
     __syncthreads();
 
-    const u32 cells = m.cells;
+    const u32 cells = a.meta ? s_c.cells : m.cells;
     const u32 lo = RANGE ? (u32)pass * a.span : 0u;
     if (RANGE && lo >= cells) return;   // this family needs fewer passes than the largest of the launch
     const u32 span = RANGE ? min(a.span, cells - lo) : cells;
@@ -861,42 +875,46 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
     slice_blocks(a.N, slice, a.S, b0, b1);
     const long long nvec = (a.N + 15) >> 4;
     const long long v0 = b0 * 32, v1 = min(b1 * 32, nvec);   // 16-row vectors of the uint8 columns
-    if (threadIdx.x == 0) {
-        // replicas pay off only when the row loop dwarfs zeroing + summing R tables:
-        // at least 16 rows per replicated counter
-        u32 R = 1;
+    // Lane replicas (every thread computes the same R; thread 0 publishes it with the rest of the
+    // decoded family before the barrier that follows the zeroing).  Replicas pay off only when the
+    // row loop dwarfs zeroing + summing R tables: at least 16 rows per replicated counter.
+    u32 R0 = 1;
+    {
         const long long rows_here = (v1 - v0) * 16;
         if (!GLOBAL && !RANGE)
-            while (R < 32 && cells * (R * 2) <= a.cap_words && cells * (R * 2) <= 16383u &&   // 16-bit lane offsets
-                   cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) && (long long)cells * (R * 2) * 16 <= rows_here)
-                R *= 2;
+            while (R0 < 32 && cells * (R0 * 2) <= a.cap_words && cells * (R0 * 2) <= 16383u &&   // 16-bit lane offsets
+                   cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) && (long long)cells * (R0 * 2) * 16 <= rows_here)
+                R0 *= 2;
         // measured (ncu source counters, tools/microbench2): R = 32 -> 1.00 wavefront per warp
         // atomic, 16 -> 2.0, none -> ~2.6, but 8 -> 2.8 and 4 -> 3.3 because interleaving then
         // confines each lane to 4 or 8 banks.  So: 32, 16 or nothing.
-        if (R < 16) R = 1;
-        m.R = R;
-        m.mul = 4u * R;
+        if (R0 < 16) R0 = 1;
+    }
+    if (a.meta && threadIdx.x < KMAX) {
+        m.par[threadIdx.x] = s_c.par[threadIdx.x];
+        m.rad[threadIdx.x] = s_c.rad[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        if (a.meta) { m.k = s_c.k; m.node = s_c.node; m.r = s_c.r; m.q = s_c.q; m.cells = s_c.cells; m.small = s_c.small; }
+        m.R = R0;
+        m.mul = 4u * R0;
         m.lo4 = lo * 4u;
         m.span4 = span * 4u;
-        s_next = 0;
     }
-    __syncthreads();
-    const u32 R = m.R;
     u32 *tab = (a.need && a.need[j]) ? a.arena + a.table_off[j] : nullptr;
-    u32 *hist = GLOBAL ? tab : s_hist + (threadIdx.x & (R - 1));
-    if (!GLOBAL) {
-        for (u32 c = threadIdx.x; c < span * R; c += THREADS) s_hist[c] = 0;
-        __syncthreads();
-    }
+    u32 *hist = GLOBAL ? tab : s_hist + (threadIdx.x & (R0 - 1));
+    if (!GLOBAL)
+        for (u32 c = threadIdx.x; c < span * R0; c += THREADS) s_hist[c] = 0;
+    __syncthreads();   // the decoded family, R and the zeroed table are visible
+    const u32 R = m.R;
 
     // packed path: all columns <= 4 states, index * mul fits 16-bit lanes.  The choice must not
     // depend on the slice, hence no R here: R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
-        u32 *next = a.dyn ? &s_next : nullptr;
-        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist, next);
-        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist, next);
-        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, next);
+        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist);
     } else if (RANGE && a.cellbuf) {
         count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
     } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.tma && m.k <= 6) {

@@ -442,28 +442,3 @@ def test_cache_checkpoint_refuses_other_content_and_bad_keys(sachs, tmp_path):
         k = np.array([[3, 0b110000], [4, 0b1]], dtype=np.uint64)
         assert lib.bic_cache_import(s._ctx, k.ctypes.data, terms.ctypes.data, nparams.ctypes.data, 2, 0) == 0
         assert s.cache_stats()["families"] == 2
-
-
-# ------------------------------ packed path with dynamically drawn row chunks (BIC_DYN=1)
-@pytest.mark.parametrize("N", [1, 63, 2047, 2049, 70_001, 1_300_000])
-def test_dynamic_row_chunks_match_fixed_stride(N, monkeypatch):
-    """The warps of a CTA draw their 32-group chunks from a shared-memory ticket instead of a fixed
-    stride: every row is still counted exactly once (counts == oracle, same score bits)."""
-    monkeypatch.setenv("BIC_PACK2_MIN_ROWS", "1")
-    rng = np.random.default_rng(N)
-    card = np.array([2, 3, 4, 4, 3, 2, 4, 3, 2], dtype=np.int32)
-    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
-    fams = [(0, []), (1, [0]), (2, [0, 1]), (3, [0, 1, 2]), (4, [0, 1, 2, 3]), (5, [0, 1, 2, 3, 4]),
-            (6, [0, 1, 2, 3, 4, 5]), (8, [1, 3, 7]), (7, [2, 3, 4, 5, 6, 8])]
-    node = np.array([f[0] for f in fams], dtype=np.int32)
-    off = np.zeros(len(fams) + 1, dtype=np.int64)
-    off[1:] = np.cumsum([len(f[1]) for f in fams])
-    par = np.array([p for f in fams for p in f[1]], dtype=np.int32)
-    with pkg.BicScorer(codes, card) as s:
-        want = s.score_families_csr(node, off, par, no_cache=True)
-    monkeypatch.setenv("BIC_DYN", "1")
-    with pkg.BicScorer(codes, card) as s:
-        tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
-        for (i, ps), t in zip(fams, tabs):
-            assert np.array_equal(t, C.family_counts(codes, card, i, ps)), (N, i, ps)
-        assert np.array_equal(s.score_families_csr(node, off, par, no_cache=True), want)
