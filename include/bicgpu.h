@@ -136,7 +136,9 @@ int bic_score_dags_csr(bic_ctx *ctx, const int64_t *off, const int32_t *parents,
  * vertex labels (BN variable index of vertex v) and n edge words, bit u of ebits[b][v] set
  * <=> edge vertex u -> vertex v (u < v); the relabel of bnlearn.py:38-42 runs on the GPU.
  * n <= 32.  DAGs whose labels are not a permutation of 0..n-1 are rejected like cyclic ones
- * (bnlearn.py:34-35 asserts). */
+ * (bnlearn.py:34-35 asserts).
+ * With BIC_FLAG_LOCAL_BATCH (any of the three DAG entry points, family sharding): B, the arrays,
+ * out[] and *n_invalid all refer to this rank's own DAGs. */
 int bic_score_dags_wire(bic_ctx *ctx, const uint8_t *labels, const uint32_t *ebits, int64_t B,
                         int metric, double *out, int64_t *n_invalid, int flags);
 /* The wire format for any n <= 1024, with the reference's own label type (l_i is uint16,
@@ -179,8 +181,8 @@ typedef struct {
     int64_t rows_counted;  /* sum over counted families of N (this rank's rows)             */
     int64_t alg_bytes;     /* sum over counted families of (k+1)*N + 4*q*r                  */
     /* the same, split by count-kernel class (0..2: shared-memory tables of <= 2048 / 12288 /
-     * 49152 cells, kernels k_count<256,false> / <512,false> / <512,false>; 3: larger tables,
-     * counted in passes over shared-memory sub-ranges, k_count<512,false,true>, when the rows
+     * 49152 cells, kernels k_count<256,false> / <512,false> / <1024,false>; 3: larger tables,
+     * counted in passes over shared-memory sub-ranges, k_count<1024,false,true>, when the rows
      * dwarf the table, else straight into HBM with L2 atomics, k_count<256,true>) */
     double class_ms[4];
     int64_t class_launches[4];
