@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libbicgpu.so")
+LIB_PATH = os.environ.get("BIC_LIB") or os.path.join(CSRC, "libbicgpu.so")   # BIC_LIB: an experimental build of the same ABI
 
 BIC_OK = 0
 FLAG_DEVICE_PTRS = 1

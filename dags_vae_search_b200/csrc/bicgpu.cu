@@ -621,6 +621,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.donor = (with_donors && n_derived) ? c->donor.as<int>() : nullptr;
     a.bd_mode = c->cache_mode;
     a.p2_vec = c->tune.p2_vec;
+    a.k30 = 1u << 30; a.k28 = 1u << 28; a.k26 = 1u << 26;
     a.tma = c->tune.tma ? 1 : 0;
     a.meta = nullptr;
     if (c->tune.park_meta && njobs <= (1ll << 22)) {   // decode every job's key once, not once per count CTA

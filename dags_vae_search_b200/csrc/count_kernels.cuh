@@ -46,6 +46,7 @@ struct CountArgs {
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
     const FamMetaC *meta;    // per job: the decoded family (k_decode_jobs), or NULL: thread 0 of every CTA decodes the key
+    u32 k30, k28, k26;       // 2^30, 2^28, 2^26 (opaque to the compiler; -DBIC_UNPACK_FMA experiment)
     int p2_vec;              // packed path: 32-bit words of a column one thread loads per iteration (4, 2 or 1)
     int bd_mode;             // 0: log-likelihood terms; 1: BDeu with imaginary sample size iss; 2: K2
     double iss;
@@ -436,12 +437,23 @@ __device__ __forceinline__ void count_rows_tma_mode(const FamMeta &m, const uint
 // four columns (radices <= 4, so < 256 combinations) form the low group, the up to three
 // columns before them the high group; both are widened to 16-bit lanes with PRMT and combined
 // as hi * (P_low * mul) + lo * mul, which is the byte offset of the counter.
-__device__ __forceinline__ void unpack2(u32 W, u32 (&u)[4]) {
+#ifdef BIC_UNPACK_FMA
+// experiment: the three shifts as IMAD.HI by 2^30 / 2^28 / 2^26 (kernel parameters, opaque to the
+// compiler) — FMA pipe instead of the ALU pipe that is at 80 %
+__device__ __forceinline__ void unpack2(u32 W, u32 (&u)[4], u32 k30, u32 k28, u32 k26) {
+    u[0] = W & 0x03030303u;
+    u[1] = __umulhi(W, k30) & 0x03030303u;
+    u[2] = __umulhi(W, k28) & 0x03030303u;
+    u[3] = __umulhi(W, k26) & 0x03030303u;
+}
+#else
+__device__ __forceinline__ void unpack2(u32 W, u32 (&u)[4], u32, u32, u32) {
     u[0] = W & 0x03030303u;
     u[1] = (W >> 2) & 0x03030303u;
     u[2] = (W >> 4) & 0x03030303u;
     u[3] = (W >> 6) & 0x03030303u;
 }
+#endif
 
 // VEC = 32-bit words (16 rows each) of every column a thread loads per iteration: 4 (one 128-bit
 // load = 64 rows), 2 or 1.  Fewer bytes in flight per thread leave more of the SM's unified
@@ -467,7 +479,7 @@ template <> struct P2Load<1> {
 
 template <int K, int VEC, bool MASKED>
 __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (&rad)[K + 1], u32 mul, u32 plow_mul,
-                                         u32 *hist, int lim) {
+                                         u32 *hist, int lim, u32 k30, u32 k28, u32 k26) {
     constexpr int C = K + 1;                  // columns, child last
     constexpr int C1 = C > 4 ? C - 4 : 0;     // columns of the high group
 #pragma unroll
@@ -476,7 +488,7 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
 #pragma unroll
         for (int a = 0; a < C; ++a) {
             u32 u[4];
-            unpack2(w[a][wd], u);
+            unpack2(w[a][wd], u, k30, k28, k26);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 if (a < C1) hi[s] = (a == 0) ? u[s] : hi[s] * rad[a] + u[s];
@@ -502,7 +514,7 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
 // [b0, b1): the CTA's slice in 512-row blocks (128 bytes of a packed column)
 template <int K, int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                              long long N, long long b0, long long b1, u32 *hist) {
+                                              long long N, long long b0, long long b1, u32 *hist, u32 k30, u32 k28, u32 k26) {
     constexpr int C = K + 1;
     constexpr int C1 = C > 4 ? C - 4 : 0;
     constexpr int ROWS = 16 * VEC;            // rows of one thread-iteration
@@ -528,22 +540,22 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
 #pragma unroll
         for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
         const long long row0 = g * ROWS;
-        if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS);
-        else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0));
+        if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS, k30, k28, k26);
+        else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0), k30, k28, k26);
     }
 }
 
 template <int THREADS, int VEC>
 __device__ __forceinline__ void count_rows_p2_k(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
-                                                long long N, long long b0, long long b1, u32 *hist) {
+                                                long long N, long long b0, long long b1, u32 *hist, u32 k30, u32 k28, u32 k26) {
     switch (m.k) {
-        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
-        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist); break;
+        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
     }
 }
 
@@ -841,10 +853,13 @@ __device__ __forceinline__ void count_rows_cells(const u32 *__restrict__ cells, 
 // shared memory, streams the slice and skips the rows whose cell lies elsewhere.  The passes of a
 // slice are neighbours in the grid, so all but the first read the rows from L2.  That trades
 // P x the streaming for shared-memory atomics instead of one L2 atomic per row (measured
-// 0.09-0.19 T/s for the whole GPU).  Superseded by k_count_cluster (one pass, table spread over a
-// thread-block cluster) where that is faster; kept for tables beyond a cluster's reach.
+// 0.09-0.19 T/s for the whole GPU).  k_count_cluster (one pass, table spread over a thread-block
+// cluster) and parked cell indices (k_cells) were both measured slower and are off by default.
+#ifndef BIC_C0_MINBLOCKS
+#define BIC_C0_MINBLOCKS 4   // 256-thread CTAs per SM the register allocation is sized for (experiment: 3 -> 80 registers)
+#endif
 template <int THREADS, bool GLOBAL, bool RANGE = false>
-__global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) k_count(CountArgs a) {   // 64 registers: 1024 threads per SM
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : THREADS > 256 ? 1024 / THREADS : 1) k_count(CountArgs a) {   // 64 registers: 1024 threads per SM
     static_assert(!(GLOBAL && RANGE), "a sub-range table lives in shared memory");
     extern __shared__ __align__(128) u32 s_hist[];
     __shared__ FamMeta m;
@@ -912,9 +927,9 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 256 ? 1024 / THREADS : 1) 
     // depend on the slice, hence no R here: R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
-        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist);
-        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist);
-        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist);
+        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+        else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+        else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
     } else if (RANGE && a.cellbuf) {
         count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
     } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.tma && m.k <= 6) {
