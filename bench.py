@@ -508,6 +508,7 @@ def main():
         per_rank = n_stream // world
         chunk = max(4096, 65536 // world)      # 65 536 DAGs per (global) call: bigger batches share and derive more families
         scorer.cache_clear()
+        scorer.cache_reserve(6_000_000)       # a search of known size reserves its cache once (growth = cudaMalloc + rehash stalls)
         scorer.profile_enable(True)
         scorer.profile_reset()
         chunks = [(c0, min(chunk, per_rank - c0)) for c0 in range(0, per_rank, chunk)]
@@ -542,7 +543,7 @@ def main():
                       "families_derived_rank0": sp["families_derived"], "cache_bytes_rank0": st["bytes"],
                       "count_ms_rank0": sp["count_ms"], "checksum_rank0": acc,
                       "note": "BASELINE configs[3] as written: ER candidates (torch-generated on the device, same recipe) scored in one "
-                              "pass with the family cache kept; every rank passes its own chunks, family-sharded over the GPUs"
+                              "pass with the family cache kept (reserved for 6 M families up front); every rank passes its own chunks, family-sharded over the GPUs"
                               if world > 1 else "BASELINE configs[3] as written: ER candidates (torch-generated on the device, same recipe) "
                               "scored in one pass with the family cache kept"}
         del cand, out_c
