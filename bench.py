@@ -783,6 +783,7 @@ def main():
         "families_derived_per_step": prof["families_derived"] / args.steps,
         "clocks": clocks,
         "checksum": checksum,
+        "build": nat.build_info(),
         "parity_note": ("parity pinned by the reference's own golden values (asia / bic: known answer + 1408 predictor targets, tests/)"
                         if cfg.get("fixture") == "asia" else
                         "parity UNPINNED for this workload: the reference holds no test, fixture or output for it; the CUDA path is "

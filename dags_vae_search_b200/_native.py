@@ -29,7 +29,7 @@ STATUS_NAMES = {
 
 # every symbol include/bicgpu.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "bic_version", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_wait_stream", "bic_sync", "bic_set_iss",
+    "bic_version", "bic_build_info", "bic_create", "bic_destroy", "bic_last_error", "bic_set_stream", "bic_wait_stream", "bic_sync", "bic_set_iss",
     "bic_dataset_fingerprint", "bic_score_dags_wire16",
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
@@ -124,6 +124,7 @@ def lib() -> ctypes.CDLL:
     L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
     L.bic_version.restype = ctypes.c_int
+    L.bic_build_info.restype = ctypes.c_char_p
     L.bic_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
     L.bic_destroy.argtypes = [vp]
     L.bic_last_error.argtypes = [vp]
@@ -153,10 +154,15 @@ def lib() -> ctypes.CDLL:
     L.bic_comm_destroy.argtypes = [vp]
     L.bic_comm_mode.argtypes = [vp, ctypes.c_int]
     for name in SYMBOLS:
-        if name not in ("bic_last_error",):
+        if name not in ("bic_last_error", "bic_build_info"):
             getattr(L, name).restype = ctypes.c_int
     _LIB = L
     return L
+
+
+def build_info() -> str:
+    """Provenance of the loaded library (ABI version, arch, compiler, build time) and its path."""
+    return lib().bic_build_info().decode() + ", " + os.path.relpath(LIB_PATH, os.path.dirname(_HERE))
 
 
 def check(ctx, status: int) -> None:

@@ -1080,6 +1080,13 @@ int bic_plan_slices(const bic_plan_in_t *in, bic_plan_out_t *out) {
 
 int bic_version(void) { return BICGPU_VERSION; }
 
+#define BIC_STR2(x) #x
+#define BIC_STR(x) BIC_STR2(x)
+const char *bic_build_info(void) {
+    return "libbicgpu ABI " BIC_STR(BICGPU_VERSION) ", sm_100a only, nvcc " BIC_STR(__CUDACC_VER_MAJOR__) "." BIC_STR(__CUDACC_VER_MINOR__) "."
+           BIC_STR(__CUDACC_VER_BUILD__) ", built " __DATE__ " " __TIME__;
+}
+
 const char *bic_last_error(const bic_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int bic_create(bic_ctx **out, int device) {

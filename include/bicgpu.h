@@ -79,6 +79,9 @@ enum {
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int bic_version(void);
+/* Build provenance: ABI version, target architecture, compiler and build time of the loaded library
+ * (bench.py prints it into its JSON line, so a measurement names the binary it was taken on). */
+const char *bic_build_info(void);
 /* Replaces: process start-up of the Rscript child (bnlearn.py:46-54). */
 int bic_create(bic_ctx **out, int device);
 int bic_destroy(bic_ctx *ctx);

@@ -30,6 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.bic_version() == 200
+    assert "sm_100a" in nat.build_info() and "ABI 200" in nat.build_info()
 
 
 def test_library_is_sm100a_only():
