@@ -144,6 +144,7 @@ struct bic_ctx {
         bool park_cells = false;               // BIC_PARK_CELLS=1: class-3 passes read the cell index of every row from scratch that k_cells
                                                //   fills once, instead of recomputing it per pass (measured slower: 0.57 vs 0.38 ms)
         long long cells_max_mb = 4096;         // BIC_CELLS_MAX_MB: scratch limit; above it the passes recompute
+        bool sort_jobs = true;                 // BIC_NO_SORT=1: count jobs run in the (arbitrary) order they were classified in
         bool park_meta = true;                 // BIC_NO_META=1: thread 0 of every count CTA decodes its family key (round-1 behaviour)
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
@@ -168,6 +169,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
             if (const char *e = getenv("BIC_NO_META")) park_meta = atoi(e) == 0;
+            if (const char *e = getenv("BIC_NO_SORT")) sort_jobs = atoi(e) == 0;
             if (const char *e = getenv("BIC_PARK_CELLS")) park_cells = atoi(e) != 0;
             if (const char *e = getenv("BIC_CELLS_MAX_MB")) { long long v = atoll(e); if (v >= 0) cells_max_mb = v; }
             if (const char *e = getenv("BIC_NO_PUSH")) push = atoi(e) == 0;
@@ -199,7 +201,7 @@ struct bic_ctx {
     u32 **d_peer = nullptr;              // device array [world] of exchange-buffer pointers (own buffer at [rank])
     int xchg_state = 0;                  // 0 not tried, 1 ready, -1 unavailable (fall back to ncclAllReduce of the tables)
     int *d_barrier = nullptr;            // 4 bytes all-reduced as the "all pushes have landed" barrier
-    DevBuf terms, gkeys, gbad, cellbuf, meta;  // staged family terms (one all-reduce), all-gathered keys / reject flags, parked cell indices (class 3)
+    DevBuf terms, gkeys, gbad, cellbuf, meta, jobs_sorted;  // staged family terms (one all-reduce), all-gathered keys / reject flags, parked cell indices (class 3)
     cudaEvent_t ev_wait = nullptr;       // bic_wait_stream
     bool fast_ok = true;     // small warm batches: try k_score_small first (off after a miss, on again after an all-hit call)
 };
@@ -646,6 +648,13 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         long long cnt = class_count[k];
         if (!cnt) continue;
         a.jobs = c->class_jobs.as<int>() + (long long)k * max_jobs;
+        if (c->tune.sort_jobs && cnt > 1 && cnt <= (1ll << 20)) {   // most parents first (k_order_jobs)
+            CU(c->jobs_sorted.ensure((size_t)max_jobs * NCLASS * sizeof(int)));
+            int *sorted = c->jobs_sorted.as<int>() + (long long)k * max_jobs;
+            k_order_jobs<<<1, 1024, 0, c->stream>>>(a.jobs, (int)cnt, keys, key_base, c->W64, sorted); LAUNCH(c);
+            CU(cudaGetLastError());
+            a.jobs = sorted;
+        }
         a.S = na.S[k];
         a.njobs = (int)cnt;
         const bool clustered = k == 3 && CL > 0;
@@ -1131,7 +1140,7 @@ int bic_destroy(bic_ctx *c) {
     DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
                       &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
                       &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_best,
-                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad, &c->cellbuf, &c->meta};
+                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad, &c->cellbuf, &c->meta, &c->jobs_sorted};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
     if (c->data2) cudaFree(c->data2);

@@ -562,6 +562,35 @@ __global__ void k_describe_direct(const u64 *__restrict__ keybuf, int W64, long 
     describe_family(keybuf + t * (W64 + 1), W64, card, N, (u32)t, max_jobs, hdr, cells_arr, class_jobs);
 }
 
+// Order the jobs of one class by their number of parents, most first (counting sort in shared
+// memory, one block).  The count kernel is ~300 KB of code in seven parent-count specialisations;
+// CTAs that are resident together then mostly run the same one (instruction cache) and take about
+// as long as their neighbours, and the long jobs start first.  Order inside a bucket is arbitrary;
+// no result depends on the job order.
+__global__ void __launch_bounds__(1024) k_order_jobs(const int *__restrict__ in, int cnt, const u64 *__restrict__ keys,
+                                                     long long key_base, int W64, int *out) {
+    __shared__ u32 s_hist[16], s_start[16];
+    if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [&](int j) {
+        const u64 *key = keys + (key_base + j) * (long long)(W64 + 1);
+        int pc = 0;
+        for (int w = 0; w < W64; ++w) pc += __popcll(key[1 + w]);
+        return min(pc, 15);
+    };
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) atomicAdd(&s_hist[bucket(in[i])], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 pos = 0;
+        for (int b = 15; b >= 0; --b) { s_start[b] = pos; pos += s_hist[b]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int j = in[i];
+        out[atomicAdd(&s_start[bucket(j)], 1u)] = j;
+    }
+}
+
 // Which jobs need their table in HBM: S > 1 slices, class 3, or the caller wants the counts.
 struct NeedArgs { int S[NCLASS]; int all; };
 __global__ void k_table_need(const u32 *__restrict__ cells_arr, u32 njobs, NeedArgs a, u32 *need) {
