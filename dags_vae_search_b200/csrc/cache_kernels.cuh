@@ -562,11 +562,13 @@ __global__ void k_describe_direct(const u64 *__restrict__ keybuf, int W64, long 
     describe_family(keybuf + t * (W64 + 1), W64, card, N, (u32)t, max_jobs, hdr, cells_arr, class_jobs);
 }
 
-// Order the jobs of one class by their number of parents, most first (counting sort in shared
-// memory, one block).  The count kernel is ~300 KB of code in seven parent-count specialisations;
-// CTAs that are resident together then mostly run the same one (instruction cache) and take about
-// as long as their neighbours, and the long jobs start first.  Order inside a bucket is arbitrary;
-// no result depends on the job order.
+// Experiment (BIC_SORT_JOBS=1, off by default): order the jobs of one class by their number of
+// parents, most first (counting sort in shared memory, one block), so that CTAs resident together
+// run the same specialisation of the ~300 KB count kernel (instruction cache) and take about as
+// long as their neighbours.  Measured 2.2 % SLOWER on the alarm-shaped step (58.4 vs 57.2 ms):
+// in the arbitrary order small replicated tables (ALU-bound) and large ones (bound by the
+// shared-memory atomic pipe) share an SM and load the two pipes more evenly.  No result depends
+// on the job order.
 __global__ void __launch_bounds__(1024) k_order_jobs(const int *__restrict__ in, int cnt, const u64 *__restrict__ keys,
                                                      long long key_base, int W64, int *out) {
     __shared__ u32 s_hist[16], s_start[16];
