@@ -442,3 +442,47 @@ def test_cache_checkpoint_refuses_other_content_and_bad_keys(sachs, tmp_path):
         k = np.array([[3, 0b110000], [4, 0b1]], dtype=np.uint64)
         assert lib.bic_cache_import(s._ctx, k.ctypes.data, terms.ctypes.data, nparams.ctypes.data, 2, 0) == 0
         assert s.cache_stats()["families"] == 2
+
+
+# ----------------------------------------------------------------- edges of the new entry points
+def test_wire16_at_the_variable_limit_and_flag_errors(asia):
+    """n = 1024 (NMAX): 32 edge words per vertex, 17-word keys; BIC_FLAG_LOCAL_BATCH without family
+    sharding and too few edge words are argument errors; bic_wait_stream accepts the legacy default
+    stream (NULL)."""
+    import torch
+    n, N = 1024, 600
+    rng = np.random.default_rng(5)
+    card = rng.integers(2, 4, size=n).astype(np.int32)
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    adj = np.zeros((3, n, n), dtype=np.uint8)
+    for b in range(3):
+        order = rng.permutation(n)
+        for _ in range(1500):
+            i, j = sorted(rng.choice(n, size=2, replace=False))
+            if adj[b][:, order[j]].sum() < 3:
+                adj[b, order[i], order[j]] = 1           # edge from an earlier to a later vertex of `order`: acyclic
+    labels, ebits = wire.from_adjacency(adj)
+    assert ebits.shape == (3, n, 32)
+    with pkg.BicScorer(codes, card) as s:
+        want = s.score_adjacency(adj)
+        assert_scores(want, C.score_dags_adj(codes, card, adj))
+        assert np.array_equal(s.score_wire(labels, ebits), want)
+        dev = s.score_wire(torch.from_numpy(labels.astype(np.int32)).cuda(), torch.from_numpy(ebits.astype(np.int64)).cuda())
+        assert np.array_equal(dev.cpu().numpy(), want)
+        lib = nat.lib()
+        out = np.zeros(3)
+        lab16 = np.ascontiguousarray(labels, dtype=np.uint16)
+        rc = lib.bic_score_dags_wire16(s._ctx, lab16.ctypes.data, ebits.ctypes.data, 31, 3, 0, out.ctypes.data, None, 0)
+        assert rc == -2 and b"ewords" in lib.bic_last_error(s._ctx)
+        rc = lib.bic_score_dags_adj(s._ctx, adj.ctypes.data, 3, 0, out.ctypes.data, None, nat.FLAG_LOCAL_BATCH)
+        assert rc == -2 and b"family sharding" in lib.bic_last_error(s._ctx)
+        assert lib.bic_wait_stream(s._ctx, None) == 0
+        assert np.array_equal(s.score_adjacency(adj), want)
+    codes_a, card_a = asia
+    with pkg.BicScorer(codes_a, card_a) as s:      # the legacy uint8 entry point still serves n <= 32
+        lab8 = np.tile(np.arange(8, dtype=np.uint8), (2, 1))
+        eb = np.zeros((2, 8), dtype=np.uint32)
+        eb[1, 3] = 0b101
+        out = np.zeros(2)
+        assert nat.lib().bic_score_dags_wire(s._ctx, lab8.ctypes.data, eb.ctypes.data, 2, 0, out.ctypes.data, None, 0) == 0
+        assert np.array_equal(out, s.score_wire(lab8, eb))
