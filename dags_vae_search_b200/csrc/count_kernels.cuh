@@ -44,6 +44,7 @@ struct CountArgs {
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
+    int u8_narrow;           // uint8 path of classes 0 / 1: 8-byte loads (experiment)
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
     const FamMetaC *meta;    // per job: the decoded family (k_decode_jobs), or NULL: thread 0 of every CTA decodes the key
     u32 k30, k28, k26;       // 2^30, 2^28, 2^26 (opaque to the compiler; -DBIC_UNPACK_FMA experiment)
@@ -355,6 +356,48 @@ __device__ __forceinline__ void cells_words(const u32 (&w)[K + 1][NW], const u32
                 for (int a = 0; a <= K; ++a) c = c * rad[a] + ((w[a][i] >> (8 * b)) & 0xffu);
                 off[i * 4 + b] = c * mul;
             }
+    }
+}
+
+// uint8 path with 8-byte loads (experiment knob BIC_U8_NARROW=1): half the bytes in flight per thread,
+// twice the load instructions — affordable where the ALU pipe has headroom (the uint8 path; on the
+// packed path narrower loads lost) and meant to make room for 48 KB class-0 tables there as well.
+template <int K, int MODE, int THREADS>
+__device__ __forceinline__ void count_rows_narrow(const FamMeta &m, const uint8_t *__restrict__ data, long long stride, long long N,
+                                                  long long v0, long long v1, u32 *hist) {
+    constexpr int C = K + 1;
+    const uint8_t *cp[C];
+    u32 rad[C];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    const u32 mul = m.mul;
+    for (long long h = v0 * 2 + threadIdx.x; h < v1 * 2; h += THREADS) {   // 8-row half vectors
+        u32 w[C][2];
+#pragma unroll
+        for (int a = 0; a < C; ++a)
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(w[a][0]), "=r"(w[a][1]) : "l"(cp[a] + h * 8));
+        u32 off[8];
+        cells_words<K, 2, MODE>(w, rad, mul, off);
+        const long long row0 = h * 8;
+        const int nv = row0 + 8 <= N ? 8 : (int)max(0ll, N - row0);
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if (b < nv) bump_off<false>(hist, off[b]);
+    }
+}
+
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_narrow_mode(const FamMeta &m, const uint8_t *__restrict__ data, long long stride, long long N,
+                                                       long long v0, long long v1, u32 *hist) {
+    switch (count_mode(m.cells, m.R)) {
+        case MODE_U8: count_rows_narrow<K, MODE_U8, THREADS>(m, data, stride, N, v0, v1, hist); break;
+        case MODE_U16: count_rows_narrow<K, MODE_U16, THREADS>(m, data, stride, N, v0, v1, hist); break;
+        default: count_rows_narrow<K, MODE_U32, THREADS>(m, data, stride, N, v0, v1, hist); break;
     }
 }
 
@@ -932,6 +975,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
         else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
     } else if (RANGE && a.cellbuf) {
         count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
+    } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.u8_narrow && m.k <= 6) {
+        switch (m.k) {
+            case 0: count_rows_narrow_mode<0, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+            case 1: count_rows_narrow_mode<1, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+            case 2: count_rows_narrow_mode<2, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+            case 3: count_rows_narrow_mode<3, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+            case 4: count_rows_narrow_mode<4, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+            case 5: count_rows_narrow_mode<5, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+            default: count_rows_narrow_mode<6, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        }
     } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.tma && m.k <= 6) {
         uint8_t *ring = reinterpret_cast<uint8_t *>(s_hist + a.cap_words);
         switch (m.k) {

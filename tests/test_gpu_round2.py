@@ -372,11 +372,13 @@ def test_bench_synthetic_v12_c2_batch():
 
 
 # ------------------------------------------- TMA-staged row tiles (experiment knob BIC_TMA=1)
+@pytest.mark.parametrize("knob", ["BIC_TMA", "BIC_U8_NARROW"])
 @pytest.mark.parametrize("N", [1, 15, 2047, 2048, 2049, 70_001, 600_000])
-def test_tma_staged_tiles_match_default_path(N, monkeypatch):
+def test_tma_staged_tiles_match_default_path(N, knob, monkeypatch):
     """uint8 path of classes 0 / 1 with the rows staged through a shared-memory ring by bulk copies
-    (cp.async.bulk + mbarrier): identical counts and score bits; ragged tails, 1..7 columns, all
-    three lane modes, a family the ring does not serve (class 2) in the same call."""
+    (cp.async.bulk + mbarrier, BIC_TMA=1) or loaded 8 bytes at a time (BIC_U8_NARROW=1): identical
+    counts and score bits; ragged tails, 1..7 columns, all three lane modes, a family the variants
+    do not serve (class 2) in the same call."""
     rng = np.random.default_rng(N)
     card = np.array([2, 3, 4, 5, 3, 2, 7, 6, 1, 3, 9, 11], dtype=np.int32)
     codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
@@ -389,7 +391,7 @@ def test_tma_staged_tiles_match_default_path(N, monkeypatch):
     par = np.array([p for f in fams for p in f[1]], dtype=np.int32)
     with pkg.BicScorer(codes, card) as s:
         want = s.score_families_csr(node, off, par, no_cache=True)
-    monkeypatch.setenv("BIC_TMA", "1")
+    monkeypatch.setenv(knob, "1")
     with pkg.BicScorer(codes, card) as s:
         tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
         for (i, ps), t in zip(fams, tabs):
