@@ -45,6 +45,7 @@ struct CountArgs {
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int u8_narrow;           // uint8 path of classes 0 / 1: 8-byte loads (experiment)
+    int u8_two;              // uint8 path, families of <= 4 columns: two row groups in flight per thread
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
     const FamMetaC *meta;    // per job: the decoded family (k_decode_jobs), or NULL: thread 0 of every CTA decodes the key
     u32 k30, k28, k26;       // 2^30, 2^28, 2^26 (opaque to the compiler; -DBIC_UNPACK_FMA experiment)
@@ -271,11 +272,57 @@ __device__ __forceinline__ void count_rows_k(const FamMeta &m, const uint8_t *__
     }
 }
 
+// The same with the loads of TWO row groups in flight per thread (columns k + 1 <= 4, so that
+// 2 (k + 1) vector registers fit): on datasets that stream from HBM the uint8 path is bound by
+// the bytes in flight, not by the data pipe (halving them with 8-byte loads cost 50 %).
+template <int K, int MODE, int THREADS>
+__device__ __forceinline__ void count_rows_k2(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                              long long N, long long v0, long long v1, u32 *hist) {
+    const uint8_t *cp[K + 1];
+    u32 rad[K + 1];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    const u32 mul = m.mul;
+    for (long long v = v0 + threadIdx.x; v < v1; v += 2 * THREADS) {
+        const long long vb = v + THREADS;
+        const bool second = vb < v1;
+        uint4 w[K + 1], wb[K + 1];
+#pragma unroll
+        for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
+#pragma unroll
+        for (int a = 0; a <= K; ++a) wb[a] = second ? ld_stream_v4(cp[a] + vb * 16) : make_uint4(0, 0, 0, 0);
+        u32 off[16];
+        if (MODE == MODE_U8) cells_u8<K>(w, rad, mul, off);
+        else if (MODE == MODE_U16) cells_u16<K>(w, rad, mul, off);
+        else cells_u32<K>(w, rad, mul, off);
+        bump16<false, false>(hist, off, v * 16, N);
+        if (second) {
+            if (MODE == MODE_U8) cells_u8<K>(wb, rad, mul, off);
+            else if (MODE == MODE_U16) cells_u16<K>(wb, rad, mul, off);
+            else cells_u32<K>(wb, rad, mul, off);
+            bump16<false, false>(hist, off, vb * 16, N);
+        }
+    }
+}
+
 template <int K, bool GLOBAL, int THREADS, bool RANGE = false>
 __device__ __forceinline__ void count_rows_mode(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
-                                                long long N, long long v0, long long v1, u32 *hist) {
+                                                long long N, long long v0, long long v1, u32 *hist, int two = 0) {
     if (GLOBAL || RANGE) {   // class 3 tables are far above the packed-lane limits
         count_rows_k<K, MODE_U32, GLOBAL, THREADS, RANGE>(m, data, stride, N, v0, v1, hist);
+        return;
+    }
+    if (K <= 3 && two) {
+        switch (count_mode(m.cells, m.R)) {
+            case MODE_U8: count_rows_k2<K <= 3 ? K : 0, MODE_U8, THREADS>(m, data, stride, N, v0, v1, hist); break;
+            case MODE_U16: count_rows_k2<K <= 3 ? K : 0, MODE_U16, THREADS>(m, data, stride, N, v0, v1, hist); break;
+            default: count_rows_k2<K <= 3 ? K : 0, MODE_U32, THREADS>(m, data, stride, N, v0, v1, hist); break;
+        }
         return;
     }
     switch (count_mode(m.cells, m.R)) {
@@ -998,10 +1045,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
         }
     } else
     switch (m.k) {
-        case 0: count_rows_mode<0, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 1: count_rows_mode<1, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 2: count_rows_mode<2, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
-        case 3: count_rows_mode<3, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
+        case 0: count_rows_mode<0, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist, a.u8_two); break;
+        case 1: count_rows_mode<1, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist, a.u8_two); break;
+        case 2: count_rows_mode<2, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist, a.u8_two); break;
+        case 3: count_rows_mode<3, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist, a.u8_two); break;
         case 4: count_rows_mode<4, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
         case 5: count_rows_mode<5, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;
         case 6: count_rows_mode<6, GLOBAL, THREADS, RANGE>(m, a.data, a.stride, a.N, v0, v1, hist); break;

@@ -372,7 +372,7 @@ def test_bench_synthetic_v12_c2_batch():
 
 
 # ------------------------------------------- TMA-staged row tiles (experiment knob BIC_TMA=1)
-@pytest.mark.parametrize("knob", ["BIC_TMA", "BIC_U8_NARROW"])
+@pytest.mark.parametrize("knob", ["BIC_TMA", "BIC_U8_NARROW", "BIC_U8_TWO"])
 @pytest.mark.parametrize("N", [1, 15, 2047, 2048, 2049, 70_001, 600_000])
 def test_tma_staged_tiles_match_default_path(N, knob, monkeypatch):
     """uint8 path of classes 0 / 1 with the rows staged through a shared-memory ring by bulk copies
