@@ -147,7 +147,10 @@ struct bic_ctx {
         bool sort_jobs = false;                // BIC_SORT_JOBS=1: count jobs of a class ordered by their number of parents (measured 2 % slower:
                                                //   co-resident CTAs of different shapes load the ALU and the shared-memory pipe more evenly)
         bool park_meta = true;                 // BIC_NO_META=1: thread 0 of every count CTA decodes its family key (round-1 behaviour)
-        bool u8_two = false;                   // BIC_U8_TWO=1: uint8 path, families of <= 4 columns keep two row groups in flight per thread
+        int u8_two = 2;                        // BIC_U8_TWO: uint8 path, families of <= 4 columns: row groups in flight per thread
+                                               //   (0 / 1: one, 2: two, 3: four / three / two for k = 0 / 1 / >= 2)
+        int p2_two = -1;                       // BIC_P2_TWO: packed path, families of <= 3 columns keep two 64-row groups in flight
+                                               //   (-1: when the packed copy is larger than L2, 0: never, 1: always)
         bool u8_narrow = false;                // BIC_U8_NARROW=1: uint8 path of classes 0 / 1 loads 8 bytes per thread per column (experiment)
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
@@ -172,7 +175,8 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_NARROW")) u8_narrow = atoi(e) != 0;
-            if (const char *e = getenv("BIC_U8_TWO")) u8_two = atoi(e) != 0;
+            if (const char *e = getenv("BIC_P2_TWO")) p2_two = atoi(e) != 0;
+            if (const char *e = getenv("BIC_U8_TWO")) { int v = atoi(e); u8_two = v <= 1 ? 0 : v >= 3 ? 3 : 2; }
             if (const char *e = getenv("BIC_NO_META")) park_meta = atoi(e) == 0;
             if (const char *e = getenv("BIC_SORT_JOBS")) sort_jobs = atoi(e) != 0;
             if (const char *e = getenv("BIC_PARK_CELLS")) park_cells = atoi(e) != 0;
@@ -631,7 +635,8 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.k30 = 1u << 30; a.k28 = 1u << 28; a.k26 = 1u << 26;
     a.tma = c->tune.tma ? 1 : 0;
     a.u8_narrow = c->tune.u8_narrow ? 1 : 0;
-    a.u8_two = c->tune.u8_two ? 1 : 0;
+    a.u8_two = c->tune.u8_two;
+    a.p2_two = c->tune.p2_two >= 0 ? c->tune.p2_two : ((long long)c->stride2 * c->n > (96ll << 20) ? 1 : 0);
     a.meta = nullptr;
     if (c->tune.park_meta && njobs <= (1ll << 22)) {   // decode every job's key once, not once per count CTA
         CU(c->meta.ensure((size_t)njobs * sizeof(FamMetaC)));

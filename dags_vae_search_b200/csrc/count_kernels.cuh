@@ -45,7 +45,8 @@ struct CountArgs {
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int u8_narrow;           // uint8 path of classes 0 / 1: 8-byte loads (experiment)
-    int u8_two;              // uint8 path, families of <= 4 columns: two row groups in flight per thread
+    int p2_two;              // packed path, families of <= 3 columns: two 64-row groups in flight per thread (datasets beyond L2)
+    int u8_two;              // uint8 path, families of <= 4 columns: row groups in flight per thread (0: one, 2: two, 3: up to four for k <= 1)
     int tma;                 // uint8 path of classes 0 / 1: rows staged through a shared-memory ring with bulk copies (experiment)
     const FamMetaC *meta;    // per job: the decoded family (k_decode_jobs), or NULL: thread 0 of every CTA decodes the key
     u32 k30, k28, k26;       // 2^30, 2^28, 2^26 (opaque to the compiler; -DBIC_UNPACK_FMA experiment)
@@ -272,11 +273,12 @@ __device__ __forceinline__ void count_rows_k(const FamMeta &m, const uint8_t *__
     }
 }
 
-// The same with the loads of TWO row groups in flight per thread (columns k + 1 <= 4, so that
-// 2 (k + 1) vector registers fit): on datasets that stream from HBM the uint8 path is bound by
-// the bytes in flight, not by the data pipe (halving them with 8-byte loads cost 50 %).
-template <int K, int MODE, int THREADS>
-__device__ __forceinline__ void count_rows_k2(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+// The same with the loads of U row groups in flight per thread (families of <= 4 columns, so that
+// U (k + 1) vector registers fit): on datasets that stream from HBM the uint8 path is bound by
+// the bytes in flight, not by the data pipe (halving them with 8-byte loads cost 50 %; doubling
+// them took the diabetes-shaped class-0 launch from 1.22 to 1.14 ms).
+template <int K, int MODE, int THREADS, int U>
+__device__ __forceinline__ void count_rows_ku(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
                                               long long N, long long v0, long long v1, u32 *hist) {
     const uint8_t *cp[K + 1];
     u32 rad[K + 1];
@@ -288,26 +290,33 @@ __device__ __forceinline__ void count_rows_k2(const FamMeta &m, const uint8_t *_
     cp[K] = data + (long long)m.node * stride;
     rad[K] = (u32)m.r;
     const u32 mul = m.mul;
-    for (long long v = v0 + threadIdx.x; v < v1; v += 2 * THREADS) {
-        const long long vb = v + THREADS;
-        const bool second = vb < v1;
-        uint4 w[K + 1], wb[K + 1];
+    for (long long v = v0 + threadIdx.x; v < v1; v += (long long)U * THREADS) {
+        uint4 w[U][K + 1];
 #pragma unroll
-        for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int a = 0; a <= K; ++a) wb[a] = second ? ld_stream_v4(cp[a] + vb * 16) : make_uint4(0, 0, 0, 0);
-        u32 off[16];
-        if (MODE == MODE_U8) cells_u8<K>(w, rad, mul, off);
-        else if (MODE == MODE_U16) cells_u16<K>(w, rad, mul, off);
-        else cells_u32<K>(w, rad, mul, off);
-        bump16<false, false>(hist, off, v * 16, N);
-        if (second) {
-            if (MODE == MODE_U8) cells_u8<K>(wb, rad, mul, off);
-            else if (MODE == MODE_U16) cells_u16<K>(wb, rad, mul, off);
-            else cells_u32<K>(wb, rad, mul, off);
-            bump16<false, false>(hist, off, vb * 16, N);
+            for (int a = 0; a <= K; ++a)
+                w[u][a] = (u == 0 || v + (long long)u * THREADS < v1) ? ld_stream_v4(cp[a] + (v + (long long)u * THREADS) * 16) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long vu = v + (long long)u * THREADS;
+            if (u == 0 || vu < v1) {
+                u32 off[16];
+                if (MODE == MODE_U8) cells_u8<K>(w[u], rad, mul, off);
+                else if (MODE == MODE_U16) cells_u16<K>(w[u], rad, mul, off);
+                else cells_u32<K>(w[u], rad, mul, off);
+                bump16<false, false>(hist, off, vu * 16, N);
+            }
         }
     }
+}
+
+template <int K, int MODE, int THREADS>
+__device__ __forceinline__ void count_rows_k2(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                              long long N, long long v0, long long v1, u32 *hist, int two) {
+    constexpr int UMAX = K == 0 ? 4 : K == 1 ? 3 : 2;
+    if (two >= 3 && UMAX > 2) count_rows_ku<K, MODE, THREADS, UMAX>(m, data, stride, N, v0, v1, hist);
+    else count_rows_ku<K, MODE, THREADS, 2>(m, data, stride, N, v0, v1, hist);
 }
 
 template <int K, bool GLOBAL, int THREADS, bool RANGE = false>
@@ -319,9 +328,9 @@ __device__ __forceinline__ void count_rows_mode(const FamMeta &m, const uint8_t 
     }
     if (K <= 3 && two) {
         switch (count_mode(m.cells, m.R)) {
-            case MODE_U8: count_rows_k2<K <= 3 ? K : 0, MODE_U8, THREADS>(m, data, stride, N, v0, v1, hist); break;
-            case MODE_U16: count_rows_k2<K <= 3 ? K : 0, MODE_U16, THREADS>(m, data, stride, N, v0, v1, hist); break;
-            default: count_rows_k2<K <= 3 ? K : 0, MODE_U32, THREADS>(m, data, stride, N, v0, v1, hist); break;
+            case MODE_U8: count_rows_k2<K <= 3 ? K : 0, MODE_U8, THREADS>(m, data, stride, N, v0, v1, hist, two); break;
+            case MODE_U16: count_rows_k2<K <= 3 ? K : 0, MODE_U16, THREADS>(m, data, stride, N, v0, v1, hist, two); break;
+            default: count_rows_k2<K <= 3 ? K : 0, MODE_U32, THREADS>(m, data, stride, N, v0, v1, hist, two); break;
         }
         return;
     }
@@ -632,6 +641,46 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
         const long long row0 = g * ROWS;
         if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow_mul, hist, ROWS, k30, k28, k26);
         else p2_group<K, VEC, true>(w, rad, mul, plow_mul, hist, (int)(N - row0), k30, k28, k26);
+    }
+}
+
+// Packed path with two 64-row groups in flight per thread (families of <= 3 columns): for packed
+// datasets that do not fit L2 (pigs-shaped: 1.4 GB) the loop is bound by the bytes in flight.
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_p2_two(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
+                                                  long long N, long long b0, long long b1, u32 *hist, u32 k30, u32 k28, u32 k26) {
+    constexpr int C = K + 1;
+    constexpr int C1 = C > 4 ? C - 4 : 0;
+    const uint8_t *cp[C];
+    u32 rad[C];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data2 + (long long)m.par[a] * stride2;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data2 + (long long)m.node * stride2;
+    rad[K] = (u32)m.r;
+    u32 plow = 1;
+#pragma unroll
+    for (int a = C1; a < C; ++a) plow *= rad[a];
+    const u32 mul = m.mul, plow_mul = plow * mul;
+    const long long g0 = b0 * 8, g1 = min(b1 * 8, (N + 63) / 64);
+    for (long long g = g0 + threadIdx.x; g < g1; g += 2 * THREADS) {
+        const long long gb = g + THREADS;
+        const bool second = gb < g1;
+        u32 w[C][4], wb[C][4];
+#pragma unroll
+        for (int a = 0; a < C; ++a) P2Load<4>::ld(cp[a] + g * 16, w[a]);
+        if (second) {
+#pragma unroll
+            for (int a = 0; a < C; ++a) P2Load<4>::ld(cp[a] + gb * 16, wb[a]);
+        }
+        if (g * 64 + 64 <= N) p2_group<K, 4, false>(w, rad, mul, plow_mul, hist, 64, k30, k28, k26);
+        else p2_group<K, 4, true>(w, rad, mul, plow_mul, hist, (int)(N - g * 64), k30, k28, k26);
+        if (second) {
+            if (gb * 64 + 64 <= N) p2_group<K, 4, false>(wb, rad, mul, plow_mul, hist, 64, k30, k28, k26);
+            else p2_group<K, 4, true>(wb, rad, mul, plow_mul, hist, (int)(N - gb * 64), k30, k28, k26);
+        }
     }
 }
 
@@ -1017,7 +1066,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     // depend on the slice, hence no R here: R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
     if (packed) {
-        if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+        if (a.p2_two && m.k <= 2) {
+            if (m.k == 0) count_rows_p2_two<0, THREADS>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+            else if (m.k == 1) count_rows_p2_two<1, THREADS>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+            else count_rows_p2_two<2, THREADS>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+        } else if (a.p2_vec == 4) count_rows_p2_k<THREADS, 4>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
         else if (a.p2_vec == 2) count_rows_p2_k<THREADS, 2>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
         else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
     } else if (RANGE && a.cellbuf) {

@@ -400,13 +400,15 @@ def test_derived_families_match_counted_ones():
 
 
 # ------------------------------------------------- 2-bit packed shadow copy of the dataset
+@pytest.mark.parametrize("two", ["0", "1"])
 @pytest.mark.parametrize("N", [1, 63, 64, 65, 511, 513, 4097, 70001])
-def test_packed_path_ragged_rows(N, monkeypatch):
+def test_packed_path_ragged_rows(N, two, monkeypatch):
     """Columns with <= 4 states are also held 4 rows per byte and streamed from there.  Force
     that path on small, ragged row counts (tail masking of the 64-row groups) and on families
     with 1..7 columns (single- and two-group index arithmetic); mixed with a 5-state column
     that must fall back to the uint8 path."""
     monkeypatch.setenv("BIC_PACK2_MIN_ROWS", "1")
+    monkeypatch.setenv("BIC_P2_TWO", two)                    # families of <= 3 columns: two 64-row groups in flight
     rng = np.random.default_rng(N)
     card = np.array([2, 3, 4, 4, 3, 2, 4, 5, 1, 3], dtype=np.int32)
     codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)

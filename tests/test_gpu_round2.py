@@ -372,7 +372,7 @@ def test_bench_synthetic_v12_c2_batch():
 
 
 # ------------------------------------------- TMA-staged row tiles (experiment knob BIC_TMA=1)
-@pytest.mark.parametrize("knob", ["BIC_TMA", "BIC_U8_NARROW", "BIC_U8_TWO"])
+@pytest.mark.parametrize("knob", ["BIC_TMA=1", "BIC_U8_NARROW=1", "BIC_U8_TWO=0", "BIC_U8_TWO=3"])
 @pytest.mark.parametrize("N", [1, 15, 2047, 2048, 2049, 70_001, 600_000])
 def test_tma_staged_tiles_match_default_path(N, knob, monkeypatch):
     """uint8 path of classes 0 / 1 with the rows staged through a shared-memory ring by bulk copies
@@ -391,7 +391,7 @@ def test_tma_staged_tiles_match_default_path(N, knob, monkeypatch):
     par = np.array([p for f in fams for p in f[1]], dtype=np.int32)
     with pkg.BicScorer(codes, card) as s:
         want = s.score_families_csr(node, off, par, no_cache=True)
-    monkeypatch.setenv(knob, "1")
+    monkeypatch.setenv(*knob.split("="))
     with pkg.BicScorer(codes, card) as s:
         tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
         for (i, ps), t in zip(fams, tabs):
