@@ -149,6 +149,32 @@ def make_dataset_gpu(cfg, rows, device, shard=0):
     return adj, card, codes
 
 
+def sort_rows_torch(codes, card, mode):
+    """Experiment knob BENCH_SORT_ROWS: the dataset's rows in lexicographic order of the variables
+    (`lex`: variable 0 most significant; `card`: highest cardinality first).  Stable LSD passes over
+    groups of variables whose mixed-radix key fits 62 bits."""
+    import torch
+    n, rows = codes.shape
+    order = list(range(n))
+    if mode == "card":
+        order = sorted(order, key=lambda v: -int(card[v]))
+    groups, cur, prod = [], [], 1
+    for v in order:
+        if prod * int(card[v]) >= (1 << 62):
+            groups.append(cur)
+            cur, prod = [], 1
+        cur.append(v)
+        prod *= int(card[v])
+    groups.append(cur)
+    perm = torch.arange(rows, device=codes.device)
+    for g in reversed(groups):
+        key = torch.zeros(rows, dtype=torch.int64, device=codes.device)
+        for v in g:
+            key = key * int(card[v]) + codes[v, perm].long()
+        perm = perm[torch.sort(key, stable=True).indices]
+    return codes[:, perm].contiguous()
+
+
 def make_dataset_cpu(cfg, rows):
     from dags_vae_search_b200 import synth
     if "fixture" in cfg:
@@ -428,6 +454,8 @@ def main():
 
     # ------------------------------------------------------------------ headline workload
     true_adj, card, codes = make_dataset_gpu(cfg, rows, device, shard=rank if sharded else 0)
+    if os.environ.get("BENCH_SORT_ROWS"):   # experiment: rows in lexicographic order (counts do not depend on the row order)
+        codes = sort_rows_torch(codes, card, os.environ["BENCH_SORT_ROWS"])
     scorer = pkg.BicScorer(codes, card, device=local_rank)
     plain_codes = codes if (famshard and not args.no_extra_legs) else None     # kept for the un-sharded reference scorer
     del codes

@@ -149,8 +149,8 @@ struct bic_ctx {
         bool park_meta = true;                 // BIC_NO_META=1: thread 0 of every count CTA decodes its family key (round-1 behaviour)
         int u8_two = 2;                        // BIC_U8_TWO: uint8 path, families of <= 4 columns: row groups in flight per thread
                                                //   (0 / 1: one, 2: two, 3: four / three / two for k = 0 / 1 / >= 2)
-        int p2_two = -1;                       // BIC_P2_TWO: packed path, families of <= 3 columns keep two 64-row groups in flight
-                                               //   (-1: when the packed copy is larger than L2, 0: never, 1: always)
+        int p2_two = 0;                        // BIC_P2_TWO=1: packed path, families of <= 3 columns keep two 64-row groups in flight
+                                               //   (experiment; pigs-shaped class-0 launch 1.033 -> 1.087 ms, 3 runs each: off)
         bool u8_narrow = false;                // BIC_U8_NARROW=1: uint8 path of classes 0 / 1 loads 8 bytes per thread per column (experiment)
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
@@ -636,7 +636,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.tma = c->tune.tma ? 1 : 0;
     a.u8_narrow = c->tune.u8_narrow ? 1 : 0;
     a.u8_two = c->tune.u8_two;
-    a.p2_two = c->tune.p2_two >= 0 ? c->tune.p2_two : ((long long)c->stride2 * c->n > (96ll << 20) ? 1 : 0);
+    a.p2_two = c->tune.p2_two;
     a.meta = nullptr;
     if (c->tune.park_meta && njobs <= (1ll << 22)) {   // decode every job's key once, not once per count CTA
         CU(c->meta.ensure((size_t)njobs * sizeof(FamMetaC)));
@@ -1048,8 +1048,13 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
         if ((flags & BIC_FLAG_NO_CYCLE_CHECK) || fmt == FMT_WIRE || fmt == FMT_WIRE16) {
             k_count_bad<<<nblk(Bc, 256), 256, 0, c->stream>>>(lbad, Bc, c->d_hdr); LAUNCH(c);
         } else {
-            if (n > 128) k_acyclic<true><<<(unsigned)Bc, ACYC_WIDE_THREADS, 0, c->stream>>>(lkeys, Bc, n, c->W64, lbad, c->d_hdr);
-            else k_acyclic<false><<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(lkeys, Bc, n, c->W64, lbad, c->d_hdr);
+            if (n > 128) {
+                const size_t mb = (size_t)n * c->W64 * sizeof(u64);
+                const int staged = mb <= ACYC_SMEM_MAX ? 1 : 0;
+                k_acyclic_wide<<<(unsigned)Bc, ACYC_WIDE_THREADS, staged ? mb : 0, c->stream>>>(lkeys, Bc, n, c->W64, lbad, c->d_hdr, staged);
+            } else {
+                k_acyclic_warp<<<nblk(Bc, ACYC_WARPS), ACYC_WARPS * 32, 0, c->stream>>>(lkeys, Bc, n, c->W64, lbad, c->d_hdr);
+            }
             LAUNCH(c);
         }
         CU(cudaGetLastError());

@@ -155,51 +155,112 @@ k_keys_wire_wide(const uint16_t *__restrict__ labels, const u32 *__restrict__ eb
 // 150 us per launch, latency-bound.
 constexpr int ACYC_WARPS = 4;
 constexpr int ACYC_WIDE_THREADS = 256;
-template <bool WIDE>
-__global__ void __launch_bounds__(WIDE ? ACYC_WIDE_THREADS : ACYC_WARPS * 32)
-k_acyclic(const u64 *__restrict__ keybuf, long long B, int n, int W64, uint8_t *dag_bad, Header *hdr) {
-    constexpr int GROUPS = WIDE ? 1 : ACYC_WARPS;
-    constexpr int LANES = WIDE ? ACYC_WIDE_THREADS : 32;
-    __shared__ u64 s_alive[GROUPS][W64MAX];
-    __shared__ u64 s_next[GROUPS][W64MAX];
-    const int grp = WIDE ? 0 : (int)(threadIdx.x >> 5), lane = WIDE ? (int)threadIdx.x : (int)(threadIdx.x & 31);
-    const long long b = (long long)blockIdx.x * GROUPS + grp;
+constexpr u32 ACYC_SMEM_MAX = 48u << 10;   // WIDE: the parent masks of a DAG are staged in shared memory when they fit
+
+// n <= 128: a warp per DAG, everything in registers.  Lane l holds the parent masks of vertices
+// l, l + 32, l + 64, l + 96 and a copy of the alive set; a peeling round is a few logic
+// instructions and one warp reduction per 32 vertices (the first version re-read the masks from
+// global memory every round: 88 us for 100 k eleven-vertex DAGs, latency-bound).
+__global__ void __launch_bounds__(ACYC_WARPS * 32)
+k_acyclic_warp(const u64 *__restrict__ keybuf, long long B, int n, int W64, uint8_t *dag_bad, Header *hdr) {
+    const int lane = (int)(threadIdx.x & 31);
+    const long long b = (long long)blockIdx.x * ACYC_WARPS + (threadIdx.x >> 5);
     if (b >= B) return;
-    auto sync = [] { if (WIDE) __syncthreads(); else __syncwarp(); };
-    int Wk = W64 + 1;
-    u64 *alive = s_alive[grp], *next = s_next[grp];
-    bool bad = dag_bad[b] != 0;        // uniform over the group
+    bool bad = dag_bad[b] != 0;   // uniform over the warp
     if (!bad) {
-        for (int w = lane; w < W64; w += LANES) {
-            int bits = min(64, n - w * 64);
-            u64 m = (bits >= 64) ? ~0ull : ((1ull << bits) - 1ull);
-            alive[w] = m;
-            next[w] = m;
-        }
-        sync();
+        const int Wk = W64 + 1;
         const u64 *keys = keybuf + b * (long long)n * Wk;
+        u64 pm[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = lane + 32 * j;
+            pm[j][0] = i < n ? keys[(long long)i * Wk + 1] : 0ull;
+            pm[j][1] = (i < n && W64 > 1) ? keys[(long long)i * Wk + 2] : 0ull;
+        }
+        u32 alive[4];   // 32 vertices per word, the same in every lane
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int bits = min(32, max(0, n - 32 * j));
+            alive[j] = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+        }
         while (true) {
-            for (int i = lane; i < n; i += LANES) {
-                if (!((alive[i >> 6] >> (i & 63)) & 1ull)) continue;
-                const u64 *pm = keys + (long long)i * Wk + 1;
-                bool blocked = false;
-                for (int w = 0; w < W64; ++w) blocked = blocked || ((pm[w] & alive[w]) != 0);
-                if (!blocked) atomicAnd(&next[i >> 6], ~(1ull << (i & 63)));
+            const u64 a0 = (u64)alive[0] | ((u64)alive[1] << 32), a1 = (u64)alive[2] | ((u64)alive[3] << 32);
+            u32 any_rm = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (32 * j >= n) break;
+                const bool mine = (alive[j] >> lane) & 1u;
+                const bool blocked = ((pm[j][0] & a0) | (pm[j][1] & a1)) != 0ull;
+                const u32 rm = __ballot_sync(0xffffffffu, mine && !blocked);
+                alive[j] &= ~rm;
+                any_rm |= rm;
             }
-            sync();
-            bool changed = false, any = false;
-            for (int w = 0; w < W64; ++w) {   // every lane reads the same words: uniform result
-                changed = changed || (next[w] != alive[w]);
-                any = any || (next[w] != 0);
+            if ((alive[0] | alive[1] | alive[2] | alive[3]) == 0u) break;
+            if (!any_rm) { bad = true; break; }
+        }
+    }
+    if (lane == 0 && bad) {
+        dag_bad[b] = 1;
+        atomicAdd(&hdr->n_invalid, 1u);
+    }
+}
+
+// Networks of more than 128 variables: one 256-thread block per DAG.  The alive set lives in shared
+// memory as 32-bit words; warp w tests the 32 vertices of words w, w + 8, ... and writes a word's
+// successor from one ballot, so a round needs no atomics (the first version cleared bits with 64-bit
+// shared-memory atomicAnd, a CAS loop: 45 us per launch of 64 DAGs of 413 vertices, most of it the
+// contention of the first rounds).  The DAG's parent masks are staged in shared memory when they fit.
+__global__ void __launch_bounds__(ACYC_WIDE_THREADS)
+k_acyclic_wide(const u64 *__restrict__ keybuf, long long B, int n, int W64, uint8_t *dag_bad, Header *hdr, int staged) {
+    extern __shared__ u64 s_masks[];   // [n][W64] when staged
+    __shared__ __align__(8) u32 s_alive[2][2 * W64MAX];
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    const long long b = blockIdx.x;
+    if (b >= B) return;
+    const int Wk = W64 + 1;
+    const int nwords = (n + 31) >> 5;
+    bool bad = dag_bad[b] != 0;        // uniform over the block
+    if (!bad) {
+        const u64 *keys = keybuf + b * (long long)n * Wk;
+        for (int w = (int)threadIdx.x; w < 2 * W64; w += ACYC_WIDE_THREADS) {
+            const int bits = min(32, max(0, n - w * 32));
+            const u32 m = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+            s_alive[0][w] = m;
+            s_alive[1][w] = m;
+        }
+        if (staged)
+            for (int x = (int)threadIdx.x; x < n * W64; x += ACYC_WIDE_THREADS) s_masks[x] = keys[(long long)(x / W64) * Wk + 1 + x % W64];
+        __syncthreads();
+        int cur = 0;
+        while (true) {
+            const u32 *alive = s_alive[cur];
+            const u64 *alive64 = reinterpret_cast<const u64 *>(alive);
+            u32 *next = s_alive[cur ^ 1];
+            u32 any_rm = 0, any_left = 0;
+            for (int wd = warp; wd < nwords; wd += ACYC_WIDE_THREADS / 32) {
+                const int i = wd * 32 + lane;
+                const u32 aw = alive[wd];
+                bool removable = false;
+                if (i < n && ((aw >> lane) & 1u)) {
+                    const u64 *pm = staged ? s_masks + (long long)i * W64 : keys + (long long)i * Wk + 1;
+                    bool blocked = false;
+                    for (int w = 0; w < W64; ++w) blocked = blocked || ((pm[w] & alive64[w]) != 0);
+                    removable = !blocked;
+                }
+                const u32 rm = __ballot_sync(0xffffffffu, removable);
+                const u32 left = aw & ~rm;
+                if (lane == 0) next[wd] = left;
+                any_rm |= rm;
+                any_left |= left;
             }
-            sync();
-            for (int w = lane; w < W64; w += LANES) alive[w] = next[w];
-            sync();
+            const int changed = __syncthreads_or((int)(any_rm != 0u));   // also publishes `next`
+            const int any = __syncthreads_or((int)(any_left != 0u));
+            cur ^= 1;
             if (!any) break;
             if (!changed) { bad = true; break; }
         }
     }
-    if (lane == 0 && bad) {
+    if (threadIdx.x == 0 && bad) {
         dag_bad[b] = 1;
         atomicAdd(&hdr->n_invalid, 1u);
     }
@@ -235,7 +296,9 @@ __global__ void k_probe(const u64 *__restrict__ keybuf, int Wk, long long T, int
         if (e & ENT_PENDING) {
             long long t2 = (long long)(e & ~ENT_PENDING);
             if (keys_equal(key, keybuf + t2 * Wk, Wk)) {
-                atomicMin(table + s, mine);
+                // the entry only ever decreases: a duplicate that cannot lower it skips the atomic (sachs: 1.1 M
+                // instances of 9 k families, most of them later in the batch than the current owner)
+                if (mine < e) atomicMin(table + s, mine);
                 inst[t] = -2 - (int)s;
                 return;
             }

@@ -644,8 +644,9 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
     }
 }
 
-// Packed path with two 64-row groups in flight per thread (families of <= 3 columns): for packed
-// datasets that do not fit L2 (pigs-shaped: 1.4 GB) the loop is bound by the bytes in flight.
+// Packed path with two 64-row groups in flight per thread (families of <= 3 columns; BIC_P2_TWO=1,
+// experiment).  Meant for packed datasets that do not fit L2 (pigs-shaped: 1.4 GB); measured 5 %
+// slower there (class-0 launch 1.033 -> 1.087 ms, three runs each), so it is off by default.
 template <int K, int THREADS>
 __device__ __forceinline__ void count_rows_p2_two(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
                                                   long long N, long long b0, long long b1, u32 *hist, u32 k30, u32 k28, u32 k26) {
@@ -1381,6 +1382,35 @@ __global__ void __launch_bounds__(THREADS) k_derive(CountArgs a, const int *__re
     const u32 nx = s_nx, xcells = s_xcells, cells = m.cells;
     const u32 t0 = (u32)((u64)cells * chunk / nchunks), t1 = (u32)((u64)cells * (chunk + 1) / nchunks);
     const int k = m.k;
+    // Few target cells, each the sum of many donor cells (a marginal of one or two variables out of
+    // a 194 k-cell donor: 21 threads walked 9261 cells each, 136 us for a launch that moves 1 MB):
+    // a warp per target cell, the lanes share out the extra cells.  Integer sums: same bits.
+    const bool wide_sum = xcells >= 64u && (t1 - t0) * 8u <= (u32)THREADS;
+    if (wide_sum) {
+        const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        for (u32 t = t0 + warp; t < t1; t += THREADS / 32) {
+            u32 rem = t / (u32)m.r;
+            size_t src = (size_t)(t - rem * (u32)m.r) * s_stride[k];
+            for (int q = k - 1; q >= 0; --q) {
+                u32 nxt = rem / m.rad[q];
+                src += (size_t)(rem - nxt * m.rad[q]) * s_stride[q];
+                rem = nxt;
+            }
+            u32 s = 0;
+            for (u32 e = lane; e < xcells; e += 32u) {
+                u32 er = e;
+                size_t o = src;
+                for (u32 ax = 0; ax < nx; ++ax) {
+                    u32 en = er / s_xrad[ax];
+                    o += (size_t)(er - en * s_xrad[ax]) * s_xstride[ax];
+                    er = en;
+                }
+                s += __ldcg(dt + o);
+            }
+            for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if (lane == 0) mt[t] = s;
+        }
+    } else
     for (u32 t = t0 + threadIdx.x; t < t1; t += THREADS) {
         u32 rem = t / (u32)m.r;
         size_t src = (size_t)(t - rem * (u32)m.r) * s_stride[k];
