@@ -151,6 +151,7 @@ struct bic_ctx {
                                                //   (0 / 1: one, 2: two, 3: four / three / two for k = 0 / 1 / >= 2)
         int p2_two = 0;                        // BIC_P2_TWO=1: packed path, families of <= 3 columns keep two 64-row groups in flight
                                                //   (experiment; pigs-shaped class-0 launch 1.033 -> 1.087 ms, 3 runs each: off)
+        bool topsplit = true;                  // BIC_TOPSPLIT=0: class-3 sub-ranges always by cell index, every pass computes the full index of every row
         bool u8_narrow = false;                // BIC_U8_NARROW=1: uint8 path of classes 0 / 1 loads 8 bytes per thread per column (experiment)
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
         bool push = true;                      // BIC_NO_PUSH=1: row-sharded runs all-reduce the count tables with NCCL instead of the
@@ -175,6 +176,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_CLUSTER_THREADS")) { int v = atoi(e); if (v == 512 || v == 1024) cluster_threads = v; }
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_NARROW")) u8_narrow = atoi(e) != 0;
+            if (const char *e = getenv("BIC_TOPSPLIT")) topsplit = atoi(e) != 0;
             if (const char *e = getenv("BIC_P2_TWO")) p2_two = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_TWO")) { int v = atoi(e); u8_two = v <= 1 ? 0 : v >= 3 ? 3 : 2; }
             if (const char *e = getenv("BIC_NO_META")) park_meta = atoi(e) == 0;
@@ -397,17 +399,18 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
     // class 3 in passes over shared-memory sub-ranges (k_count<1024, false, true>) when every table
     // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
     const long long span = CLASS2_CELLS;
-    const int P3 = (int)((in.max_cells + span - 1) / span);
+    const int P3gen = (int)((in.max_cells + span - 1) / span);
+    const int P3 = std::max(P3gen, (int)in.passes3);   // top split (range_plan) never needs more passes than the generic cut today
     // One pass over a thread-block cluster whose CTAs share the table (k_count_cluster) when it fits
     // 8 x 192 KB of distributed shared memory; else sub-range passes; else (few rows) L2 atomics.
     int CL = 0;
-    if (in.class_count[3] > 0 && tune.cluster && P3 <= 8 && in.N >= 4ll * in.max_cells) {
+    if (in.class_count[3] > 0 && tune.cluster && P3gen <= 8 && in.N >= 4ll * in.max_cells) {
         CL = 2;
-        while (CL < P3) CL *= 2;
+        while (CL < P3gen) CL *= 2;
         if (tune.cluster_size > CL) CL = tune.cluster_size;
     }
     out.cluster = CL;
-    const bool ranged = CL == 0 && in.class_count[3] > 0 && tune.range_passes > 0 && P3 <= tune.range_passes &&
+    const bool ranged = CL == 0 && in.class_count[3] > 0 && tune.range_passes > 0 && P3gen <= tune.range_passes &&
                         in.N >= 4ll * in.max_cells;
     out.ranged = ranged ? 1 : 0;
     out.passes = ranged ? P3 : 1;
@@ -588,6 +591,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     na.all = all_tables ? 1 : 0;
     bic_plan_in_t pin;
     pin.sm_count = c->sm_count; pin.N = c->N; pin.n = c->n; pin.max_cells = h.max_cells; pin.tables_in_hbm = all_tables ? 1 : 0; pin.all_packed = c->all_packed ? 1 : 0;
+    pin.passes3 = (c->tune.topsplit && !c->tune.park_cells) ? (int)h.max_passes3 : 0;
     for (int k = 0; k < NCLASS; ++k) {
         pin.class_count[k] = h.class_count[k];
         pin.class_cells[k] = (long long)h.class_cells[k];
@@ -635,6 +639,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.k30 = 1u << 30; a.k28 = 1u << 28; a.k26 = 1u << 26;
     a.tma = c->tune.tma ? 1 : 0;
     a.u8_narrow = c->tune.u8_narrow ? 1 : 0;
+    a.topsplit = (c->tune.topsplit && !c->tune.park_cells) ? 1 : 0;   // the parked cell indices follow the generic cut
     a.u8_two = c->tune.u8_two;
     a.p2_two = c->tune.p2_two;
     a.meta = nullptr;
@@ -670,7 +675,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         a.S = na.S[k];
         a.njobs = (int)cnt;
         const bool clustered = k == 3 && CL > 0;
-        a.P = (k == 3 && ranged) ? P3 : 1;
+        a.P = (k == 3 && ranged) ? P3 : 1;   // launch-wide: the family with the most sub-ranges
         a.span = span;
         long long items = cnt * a.S * a.P;
         if (items * (clustered ? CL : 1) > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");

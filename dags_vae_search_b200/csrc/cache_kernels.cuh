@@ -406,6 +406,7 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
     u64 r = (u64)card[node];
     u64 q = 1;
     int k = 0;
+    u32 rad0 = 1;   // states of the first parent (the most significant digit of the cell index)
     bool over = false;
     for (int w = 0; w < W64; ++w) {
         u64 m = key[1 + w];
@@ -414,6 +415,7 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
             m &= m - 1;
             u64 c = (u64)card[w * 64 + b];
             if (c > 1) {
+                if (k == 0) rad0 = (u32)c;
                 ++k;
                 q *= c;
                 if (q > MAX_CELLS) { over = true; q = MAX_CELLS + 1; }
@@ -434,6 +436,7 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
     atomicAdd(&hdr->alg_bytes[cls], (u64)(k + 1) * (u64)N + 4ull * cells);
     atomicAdd(&hdr->class_cells[cls], cells);
     atomicMax(&hdr->max_cells, (u32)cells);
+    if (cls == 3) atomicMax(&hdr->max_passes3, range_plan((u32)cells, k, rad0, CLASS2_CELLS, true).passes);
 }
 
 // Owners of PENDING entries take id = base + rank, publish their key in the registry and

@@ -44,6 +44,7 @@ struct CountArgs {
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
+    int topsplit;            // RANGE kernel: sub-ranges along the first parent's states where range_plan() allows it
     int u8_narrow;           // uint8 path of classes 0 / 1: 8-byte loads (experiment)
     int p2_two;              // packed path, families of <= 3 columns: two 64-row groups in flight per thread (datasets beyond L2)
     int u8_two;              // uint8 path, families of <= 4 columns: row groups in flight per thread (0: one, 2: two, 3: up to four for k <= 1)
@@ -317,6 +318,65 @@ __device__ __forceinline__ void count_rows_k2(const FamMeta &m, const uint8_t *_
     constexpr int UMAX = K == 0 ? 4 : K == 1 ? 3 : 2;
     if (two >= 3 && UMAX > 2) count_rows_ku<K, MODE, THREADS, UMAX>(m, data, stride, N, v0, v1, hist);
     else count_rows_ku<K, MODE, THREADS, 2>(m, data, stride, N, v0, v1, hist);
+}
+
+// Class 3, top split (range_plan in common.cuh): the CTA owns the states [s0, s0 + ns) of the first
+// parent.  The index below that parent (< 16384 cells) is built on 16-bit packed lanes exactly as
+// cells_u16 does for the smaller classes; the first parent costs one byte extraction, one compare
+// and one IMAD per row, and rows of other states stop there.  hist = the CTA's sub-range, cell
+// (s - s0) * low + rest at byte offset 4 * that.
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_top(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                               long long N, long long v0, long long v1, u32 *hist, u32 s0, u32 ns, u32 low4) {
+    static_assert(K >= 1, "the first parent is the split axis");
+    const uint8_t *cp[K + 1];
+    u32 rad[K + 1];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    for (long long v = v0 + threadIdx.x; v < v1; v += THREADS) {
+        uint4 w[K + 1];
+#pragma unroll
+        for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
+        u32 acc[8];
+#pragma unroll
+        for (int a = 1; a <= K; ++a) {
+            const u32 ws[4] = {w[a].x, w[a].y, w[a].z, w[a].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                u32 lo = __byte_perm(ws[i], 0u, 0x4140u);   // rows 4i, 4i+1 in 16-bit lanes
+                u32 hi = __byte_perm(ws[i], 0u, 0x4342u);   // rows 4i+2, 4i+3
+                if (a == 1) {
+                    acc[2 * i] = lo;
+                    acc[2 * i + 1] = hi;
+                } else {
+                    acc[2 * i] = acc[2 * i] * rad[a] + lo;   // lanes stay < 16384
+                    acc[2 * i + 1] = acc[2 * i + 1] * rad[a] + hi;
+                }
+            }
+        }
+        u32 off[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            u32 a4 = acc[i] * 4u;                            // lanes <= 65532
+            off[2 * i] = a4 & 0xffffu;
+            off[2 * i + 1] = a4 >> 16;
+        }
+        const u32 ts[4] = {w[0].x, w[0].y, w[0].z, w[0].w};
+        const long long row0 = v * 16;
+        const int nv = row0 + 16 <= N ? 16 : (int)(N - row0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const u32 d = __byte_perm(ts[i], 0u, 0x4440u + b) - s0;
+                if (4 * i + b < nv && d < ns) bump_off<false>(hist, d * low4 + off[4 * i + b]);
+            }
+    }
 }
 
 template <int K, bool GLOBAL, int THREADS, bool RANGE = false>
@@ -1023,9 +1083,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     __syncthreads();
 
     const u32 cells = a.meta ? s_c.cells : m.cells;
-    const u32 lo = RANGE ? (u32)pass * a.span : 0u;
+    // RANGE: this family's sub-ranges (generic cut, or runs of states of the first parent)
+    RangePlan rp;
+    rp.span = a.span; rp.passes = 1; rp.ns = 0;
+    u32 low = 0;   // top split: cells below the first parent
+    if (RANGE) {
+        const int kk = a.meta ? s_c.k : m.k;
+        const u32 rad0 = kk > 0 ? (a.meta ? (u32)s_c.rad[0] : m.rad[0]) : 1u;
+        rp = range_plan(cells, kk, rad0, a.span, a.topsplit != 0);
+        low = rp.ns ? cells / rad0 : 0u;
+    }
+    const u32 lo = RANGE ? (u32)pass * rp.span : 0u;
     if (RANGE && lo >= cells) return;   // this family needs fewer passes than the largest of the launch
-    const u32 span = RANGE ? min(a.span, cells - lo) : cells;
+    const u32 span = RANGE ? min(rp.span, cells - lo) : cells;
     long long b0, b1;
     slice_blocks(a.N, slice, a.S, b0, b1);
     const long long nvec = (a.N + 15) >> 4;
@@ -1076,6 +1146,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
         else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
     } else if (RANGE && a.cellbuf) {
         count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
+    } else if (RANGE && rp.ns) {
+        const u32 s0 = (u32)pass * rp.ns, nsh = span / low;   // the last pass may hold fewer states
+        switch (m.k) {
+            case 1: count_rows_top<1, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, s0, nsh, low * 4u); break;
+            case 2: count_rows_top<2, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, s0, nsh, low * 4u); break;
+            case 3: count_rows_top<3, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, s0, nsh, low * 4u); break;
+            case 4: count_rows_top<4, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, s0, nsh, low * 4u); break;
+            case 5: count_rows_top<5, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, s0, nsh, low * 4u); break;
+            default: count_rows_top<6, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, s0, nsh, low * 4u); break;
+        }
     } else if (!GLOBAL && !RANGE && THREADS <= 512 && a.u8_narrow && m.k <= 6) {
         switch (m.k) {
             case 0: count_rows_narrow_mode<0, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist); break;
@@ -1128,7 +1208,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     if (single) {
         ll = family_term<false>(a, s_hist, m, s_red);
     } else {
-        const u32 parts = RANGE ? (u32)a.S * ((cells + a.span - 1) / a.span) : (u32)a.S;
+        const u32 parts = RANGE ? (u32)a.S * rp.passes : (u32)a.S;
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) s_last = (atomicAdd(a.done + j, 1u) == parts - 1);

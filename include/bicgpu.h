@@ -222,6 +222,9 @@ typedef struct {
     int64_t class_alg_bytes[4];/* sum of (k+1)*N + 4*q*r per class                              */
     int32_t all_packed;        /* 1: every column also has a 2-bit packed copy that the families *
                                 * stream instead (a quarter of the bytes per row)               */
+    int32_t passes3;           /* most sub-range passes a class-3 family of the batch needs      *
+                                * (sub-ranges may follow the first parent's states);            *
+                                * 0: ceil(max_cells / 49152)                                    */
 } bic_plan_in_t;
 typedef struct {
     int32_t slices[4];         /* row slices per family, per class                              */

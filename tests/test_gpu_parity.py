@@ -493,6 +493,50 @@ def test_class3_cluster_passes_and_l2_atomics_match_oracle(monkeypatch):
     assert np.array_equal(run(), ranged)                      # L2 atomics
 
 
+def test_class3_top_split_matches_generic_cut(monkeypatch):
+    """Class-3 sub-ranges along the states of the first parent (range_plan in csrc/common.cuh: the
+    pass tests that parent's byte alone and builds the rest of the index on 16-bit packed lanes)
+    against the generic cut by cell index (BIC_TOPSPLIT=0): k = 1 .. 6 parents, a last pass with
+    fewer states, a family whose table below the first parent is too large for the split, ragged
+    row count.  Counts must equal the oracle's, scores must be the same bits either way."""
+    N = 1_300_003
+    rng = np.random.default_rng(78)
+    card = np.array([3, 250, 240, 21, 20, 6, 5, 4, 2], dtype=np.int32)
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    codes[5] = (codes[3] + codes[4]) % 6                      # structure: not every cell is hit equally
+    codes[1] = np.minimum(codes[1], rng.integers(0, 250, size=N)).astype(np.uint8)   # skewed first parent
+    fams = [(2, [1]),                                         # k = 1: 250 x 240 = 60 000 cells, 2 passes of 125 states
+            (3, [1, 4]),                                      # k = 2: 250 x 20 x 21 = 105 000 cells, 3 passes of 84 states
+            (8, [1, 3, 4]),                                   # k = 3: 250 x 21 x 20 x 2 = 210 000 cells, 5 passes
+            (7, [3, 4, 5, 6]),                                # k = 4: 21 x 20 x 6 x 5 x 4 = 50 400 cells, passes of 11 and 10 states
+            (7, [3, 4, 5, 6, 8]),                             # k = 5: 201 600 cells, 5 passes of 5 states (the last holds one)
+            (0, [3, 4, 5, 6, 7, 8]),                          # k = 6: 302 400 cells, 7 passes of 3 states
+            (8, [0, 3, 4, 5, 6, 7]),                          # k = 6, first parent has 3 states, 100 800 cells below it: no split
+            (4, [0, 2, 3])]                                   # k = 3, 3 x 240 x 21 x 20 = 302 400 cells: no split either
+    node, off, par = csr_of(fams)
+    want_tabs = [C.family_counts(codes, card, i, ps) for i, ps in fams]
+    want_scores = C.score_families(codes, card, node, off, par)
+
+    def run():
+        with pkg.BicScorer(codes, card) as s:
+            tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+            for (i, ps), t, w in zip(fams, tabs, want_tabs):
+                assert t.sum() == N
+                assert np.array_equal(t, w), (i, ps)
+            scores = s.score_families_csr(node, off, par, no_cache=True)
+            alone = s.score_families([7], [[3, 4, 5, 6, 8]], no_cache=True)      # alone: several row slices
+            assert alone[0] == scores[4]
+        assert_scores(scores, want_scores)
+        return scores
+
+    split = run()
+    monkeypatch.setenv("BIC_TOPSPLIT", "0")
+    assert np.array_equal(run(), split)
+    monkeypatch.delenv("BIC_TOPSPLIT")
+    monkeypatch.setenv("BIC_CLASS2_THREADS", "512")          # k_count<512, false, true>
+    assert np.array_equal(run(), split)
+
+
 def test_slice_choice_does_not_change_bits(monkeypatch):
     """The number of row slices per family is a cost decision (L2 windows vs merge traffic);
     counts are integer sums and the fp64 reduce has a fixed order, so any choice gives the same
