@@ -133,6 +133,8 @@ struct bic_ctx {
         u32 class0_words = CLASS0_WORDS;       // BIC_CLASS0_WORDS: shared-memory words of a class-0 CTA (uint8 path)
         u32 class0_words_packed = CLASS0_WORDS_PACKED;   // the same when every column streams from the 2-bit packed copy
         int class0_threads = 256;              // BIC_CLASS0_THREADS: 256, 512 or 1024
+        bool class0_wide = true;               // BIC_CLASS0_WIDE=0: never the 512-thread x 96 KB class-0 shape
+        bool class0_explicit = false;          // BIC_CLASS0_WORDS / BIC_CLASS0_THREADS given: no automatic wide shape (class0_shape)
         int range_passes = 8;                  // BIC_RANGE_PASSES: class-3 tables of up to this many shared-memory sub-ranges
                                                //   are counted in passes (0: always straight into HBM with L2 atomics)
         int class1_threads = 512;              // BIC_CLASS1_THREADS: 256, 512 or 1024 (48 KB tables)
@@ -151,6 +153,7 @@ struct bic_ctx {
                                                //   (0 / 1: one, 2: two, 3: four / three / two for k = 0 / 1 / >= 2)
         int p2_two = 0;                        // BIC_P2_TWO=1: packed path, families of <= 3 columns keep two 64-row groups in flight
                                                //   (experiment; pigs-shaped class-0 launch 1.033 -> 1.087 ms, 3 runs each: off)
+        bool swizzle = true;                   // BIC_SWIZZLE=0: un-replicated shared-memory tables in plain cell order
         bool topsplit = true;                  // BIC_TOPSPLIT=0: class-3 sub-ranges always by cell index, every pass computes the full index of every row
         bool u8_narrow = false;                // BIC_U8_NARROW=1: uint8 path of classes 0 / 1 loads 8 bytes per thread per column (experiment)
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
@@ -166,7 +169,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_PACK2_MIN_ROWS")) pack2_min_rows = atoll(e);
             if (const char *e = getenv("BIC_L2_WINDOW_MB")) { long long mb = atoll(e); if (mb > 0) l2_window = mb << 20; }
             if (const char *e = getenv("BIC_L2_WINDOW_MAX_MB")) { long long mb = atoll(e); if (mb > 0) l2_window_max = mb << 20; }
-            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 49152) { class0_words = (u32)w; class0_words_packed = (u32)w; } }
+            if (const char *e = getenv("BIC_CLASS0_WORDS")) { int w = atoi(e); if (w >= (int)CLASS0_CELLS && w <= 49152) { class0_words = (u32)w; class0_words_packed = (u32)w; class0_explicit = true; } }
             if (const char *e = getenv("BIC_RANGE_PASSES")) { int v = atoi(e); if (v >= 0 && v <= 64) range_passes = v; }
             if (const char *e = getenv("BIC_CLASS1_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) class1_threads = t; }
             if (const char *e = getenv("BIC_CLASS2_THREADS")) { int t = atoi(e); if (t == 512 || t == 1024) class2_threads = t; }
@@ -177,6 +180,7 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_NARROW")) u8_narrow = atoi(e) != 0;
             if (const char *e = getenv("BIC_TOPSPLIT")) topsplit = atoi(e) != 0;
+            if (const char *e = getenv("BIC_SWIZZLE")) swizzle = atoi(e) != 0;
             if (const char *e = getenv("BIC_P2_TWO")) p2_two = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_TWO")) { int v = atoi(e); u8_two = v <= 1 ? 0 : v >= 3 ? 3 : 2; }
             if (const char *e = getenv("BIC_NO_META")) park_meta = atoi(e) == 0;
@@ -188,7 +192,8 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_XCHG_MB")) { long long v = atoll(e); if (v > 0 && v <= 4096) xchg_mb = v; }
             if (const char *e = getenv("BIC_NO_FAST_SMALL")) fast_small = atoi(e) == 0;
             if (const char *e = getenv("BIC_SLICE_MODEL")) slice_model = atoi(e) != 0;
-            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) class0_threads = t; }
+            if (const char *e = getenv("BIC_CLASS0_WIDE")) class0_wide = atoi(e) != 0;
+            if (const char *e = getenv("BIC_CLASS0_THREADS")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) { class0_threads = t; class0_explicit = true; } }
         }
     } tune;
     Header *d_hdr = nullptr, *h_hdr = nullptr;
@@ -391,11 +396,31 @@ int refresh_ntotal(bic_ctx *c) {
 // into HBM with one L2 atomic per non-zero cell.  Versions a-h always cut into 32 MB windows; for
 // 64 diabetes-shaped local-move candidates (5 GB of rows, a few dozen large-table families) that
 // meant 162 slices whose merges cost 3x the counting itself.  Never under 64K rows per slice.
+// CTA shape of class 0 (tables of <= 2048 cells).  256 threads x 24 KB on the uint8 path, x 48 KB when
+// every column streams from the 2-bit packed copy.  Since the packed path builds its counter offsets
+// in 32 bits (IDP.4A) lane replicas are no longer capped at cells * R <= 16383, and for batches whose
+// class-0 tables are mostly mid-size (mean >= 256 cells: the alarm-shaped candidates, 250 - 2000
+// cells) 512 threads sharing 96 KB (32 replicas up to 768 cells, 16 up to 1536; still 1024 threads
+// per SM) cut the class-0 launch from 51.5 to 45.2 ms: by then the shared-memory data pipe was the
+// limiter (91 %, half of its atomic wavefronts bank conflicts).  Tiny tables (pigs-shaped: <= 81
+// cells) already run with 32 replicas and keep the small CTAs.
+constexpr u32 CLASS0_WORDS_WIDE = 24576;
+void class0_shape(bool all_packed, long long count0, long long cells0, const bic_ctx::Tuning &tune, int &threads, u32 &words) {
+    threads = tune.class0_threads;
+    words = all_packed ? tune.class0_words_packed : tune.class0_words;
+    if (all_packed && !tune.class0_explicit && tune.class0_wide && count0 > 0 && cells0 >= 256 * count0) {
+        threads = 512;
+        words = CLASS0_WORDS_WIDE;
+    }
+}
+
 void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_out_t &out) {
     const long long smax = std::max<long long>(1, in.N / 65536);
     // measured on B200 (profiles/): streaming loads, L2 atomics, rows per second one CTA counts, CTA set-up
     const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9, CTA_SETUP_S = 4.0e-6;
-    const long long resident[NCLASS] = {4, 2, 1, 4};   // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
+    int c0t; u32 c0w;
+    class0_shape(in.all_packed != 0, in.class_count[0], in.class_cells[0], tune, c0t, c0w);
+    const long long resident[NCLASS] = {1024 / c0t, 2, 1, 4};   // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
     // class 3 in passes over shared-memory sub-ranges (k_count<1024, false, true>) when every table
     // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
     const long long span = CLASS2_CELLS;
@@ -639,6 +664,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.k30 = 1u << 30; a.k28 = 1u << 28; a.k26 = 1u << 26;
     a.tma = c->tune.tma ? 1 : 0;
     a.u8_narrow = c->tune.u8_narrow ? 1 : 0;
+    a.swizzle = c->tune.swizzle ? 1 : 0;
     a.topsplit = (c->tune.topsplit && !c->tune.park_cells) ? 1 : 0;   // the parked cell indices follow the generic cut
     a.u8_two = c->tune.u8_two;
     a.p2_two = c->tune.p2_two;
@@ -693,8 +719,9 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         }
         // shared memory per CTA: class 0 gets several times its largest table so that small tables
         // run with 32 or 16 bank-interleaved lane replicas (conflict-free atomics).
-        const int c0t = c->tune.class0_threads;
-        const u32 cap[NCLASS] = {c->all_packed ? c->tune.class0_words_packed : c->tune.class0_words, CLASS1_CELLS, CLASS2_CELLS, 0};
+        int c0t; u32 c0w;
+        class0_shape(c->all_packed, (long long)h.class_count[0], (long long)h.class_cells[0], c->tune, c0t, c0w);
+        const u32 cap[NCLASS] = {c0w, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
         const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
         const u32 clwords = clustered ? (u32)((max_cells + CL - 1) / CL) : 0;

@@ -44,6 +44,7 @@ struct CountArgs {
     int reduce;              // 0: count only (row-sharded: reduce after the all-reduce)
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
+    int swizzle;             // packed path, un-replicated tables: bank swizzle of the cell index (swz_off)
     int topsplit;            // RANGE kernel: sub-ranges along the first parent's states where range_plan() allows it
     int u8_narrow;           // uint8 path of classes 0 / 1: 8-byte loads (experiment)
     int p2_two;              // packed path, families of <= 3 columns: two 64-row groups in flight per thread (datasets beyond L2)
@@ -165,6 +166,13 @@ __device__ __forceinline__ void bump_off(u32 *hist, u32 byte_off) {
     atomicAdd(reinterpret_cast<u32 *>(reinterpret_cast<char *>(hist) + byte_off), 1u);   // ATOMS.POPC.INC / RED
 }
 
+// Bank swizzle of un-replicated tables: slot = cell ^ ((cell >> 5) & 31), applied to the byte offset.
+// A warp's 32 increments then spread over the banks by ten index bits instead of five: the low
+// digits alone (child and last parent, often dominated by one or two states) left class-1 tables at
+// 4.1 wavefronts per warp atomic, 75 % of them bank conflicts (ncu).  The table is put back in
+// order before it is merged or reduced (unswizzle_table).
+__device__ __forceinline__ u32 swz_off(u32 off) { return off ^ ((off >> 5) & 0x7cu); }
+
 // byte offsets of the 16 rows of a group, in row order; rows >= N are skipped.  RANGE: the CTA
 // owns the cells [lo4, lo4 + span4) (byte offsets) of a table too large for shared memory and
 // ignores the rows that fall outside (another pass counts them).
@@ -201,7 +209,7 @@ __device__ __forceinline__ void cells_u8(const uint4 (&w)[K + 1], const u32 (&ra
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) off[i * 4 + b] = __byte_perm(acc[i], 0u, 0x4440u + b) * mul;
+        for (int b = 0; b < 4; ++b) off[i * 4 + b] = __dp4a(acc[i], mul << (8 * b), 0u);   // byte b * mul in one IDP.4A (mul <= 128)
 }
 
 template <int K>
@@ -642,7 +650,7 @@ template <> struct P2Load<1> {
 #ifndef BIC_P2_DP4A
 #define BIC_P2_DP4A 1
 #endif
-template <int K, int VEC, bool MASKED>
+template <int K, int VEC, bool MASKED, bool SWZ = false>
 __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (&rad)[K + 1], u32 mul, u32 plow, u32 plow_mul,
                                          u32 *hist, int lim, u32 k30, u32 k28, u32 k26) {
     constexpr int C = K + 1;                  // columns, child last
@@ -706,7 +714,10 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
             for (int s = 0; s < 4; ++s)
 #pragma unroll
                 for (int B = 0; B < 4; ++B)
-                    if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, __dp4a(lo[s], mul << (8 * B), 0u));
+                    if (!MASKED || (16 * wd + 4 * B + s) < lim) {
+                        const u32 o = __dp4a(lo[s], mul << (8 * B), 0u);
+                        bump_off<false>(hist, SWZ ? swz_off(o) : o);
+                    }
         } else if (plow < 256u) {
             const u32 wv = 1u | (plow << 8);
 #pragma unroll
@@ -717,7 +728,7 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
                                     __dp4a(v23, wv, 0u) * mul, __dp4a(v23, wv << 16, 0u) * mul};
 #pragma unroll
                 for (int B = 0; B < 4; ++B)
-                    if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, off[B]);
+                    if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, SWZ ? swz_off(off[B]) : off[B]);
             }
         } else {
 #pragma unroll
@@ -727,7 +738,7 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
                 const u32 off[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
 #pragma unroll
                 for (int B = 0; B < 4; ++B)
-                    if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, off[B]);
+                    if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, SWZ ? swz_off(off[B]) : off[B]);
             }
         }
 #else
@@ -742,14 +753,14 @@ __device__ __forceinline__ void p2_group(const u32 (&w)[K + 1][VEC], const u32 (
             const u32 off[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
 #pragma unroll
             for (int B = 0; B < 4; ++B)
-                if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, off[B]);
+                if (!MASKED || (16 * wd + 4 * B + s) < lim) bump_off<false>(hist, SWZ ? swz_off(off[B]) : off[B]);
         }
 #endif
     }
 }
 
 // [b0, b1): the CTA's slice in 512-row blocks (128 bytes of a packed column)
-template <int K, int THREADS, int VEC>
+template <int K, int THREADS, int VEC, bool SWZ = false>
 __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
                                               long long N, long long b0, long long b1, u32 *hist, u32 k30, u32 k28, u32 k26) {
     constexpr int C = K + 1;
@@ -777,8 +788,8 @@ __device__ __forceinline__ void count_rows_p2(const FamMeta &m, const uint8_t *_
 #pragma unroll
         for (int a = 0; a < C; ++a) P2Load<VEC>::ld(cp[a] + g * (4 * VEC), w[a]);
         const long long row0 = g * ROWS;
-        if (row0 + ROWS <= N) p2_group<K, VEC, false>(w, rad, mul, plow, plow_mul, hist, ROWS, k30, k28, k26);
-        else p2_group<K, VEC, true>(w, rad, mul, plow, plow_mul, hist, (int)(N - row0), k30, k28, k26);
+        if (row0 + ROWS <= N) p2_group<K, VEC, false, SWZ>(w, rad, mul, plow, plow_mul, hist, ROWS, k30, k28, k26);
+        else p2_group<K, VEC, true, SWZ>(w, rad, mul, plow, plow_mul, hist, (int)(N - row0), k30, k28, k26);
     }
 }
 
@@ -823,17 +834,17 @@ __device__ __forceinline__ void count_rows_p2_two(const FamMeta &m, const uint8_
     }
 }
 
-template <int THREADS, int VEC>
+template <int THREADS, int VEC, bool SWZ = false>
 __device__ __forceinline__ void count_rows_p2_k(const FamMeta &m, const uint8_t *__restrict__ data2, long long stride2,
                                                 long long N, long long b0, long long b1, u32 *hist, u32 k30, u32 k28, u32 k26) {
     switch (m.k) {
-        case 0: count_rows_p2<0, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
-        case 1: count_rows_p2<1, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
-        case 2: count_rows_p2<2, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
-        case 3: count_rows_p2<3, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
-        case 4: count_rows_p2<4, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
-        case 5: count_rows_p2<5, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
-        default: count_rows_p2<6, THREADS, VEC>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 0: count_rows_p2<0, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 1: count_rows_p2<1, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 2: count_rows_p2<2, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 3: count_rows_p2<3, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 4: count_rows_p2<4, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        case 5: count_rows_p2<5, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
+        default: count_rows_p2<6, THREADS, VEC, SWZ>(m, data2, stride2, N, b0, b1, hist, k30, k28, k26); break;
     }
 }
 
@@ -1184,8 +1195,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     u32 R0 = 1;
     {
         const long long rows_here = (v1 - v0) * 16;
+        // The packed path builds its counter offsets in 32 bits (p2_group, IDP.4A) unless the four low
+        // columns have four states each; everything else carries them on 16-bit lanes: cells * R <= 16383.
+        bool wide_off = false;
+#if BIC_P2_DP4A
+        if (!GLOBAL && !RANGE && a.data2 != nullptr) {
+            const int kk = a.meta ? s_c.k : m.k;
+            const bool sm = a.meta ? s_c.small != 0 : m.small != 0;
+            if (sm && kk <= 6 && cells <= 16383u) {
+                u32 plow = (u32)(a.meta ? s_c.r : m.r);
+                for (int i = kk > 3 ? kk - 3 : 0; i < kk; ++i) plow *= a.meta ? (u32)s_c.rad[i] : m.rad[i];
+                wide_off = kk < 4 || plow < 256u;
+            }
+        }
+#endif
         if (!GLOBAL && !RANGE)
-            while (R0 < 32 && cells * (R0 * 2) <= a.cap_words && cells * (R0 * 2) <= 16383u &&   // 16-bit lane offsets
+            while (R0 < 32 && cells * (R0 * 2) <= a.cap_words && (wide_off || cells * (R0 * 2) <= 16383u) &&   // 16-bit lane offsets
                    cells <= (u32)(REPL_MAX_PER_THREAD * THREADS) && (long long)cells * (R0 * 2) * 16 <= rows_here)
                 R0 *= 2;
         // measured (ncu source counters, tools/microbench2): R = 32 -> 1.00 wavefront per warp
@@ -1207,14 +1232,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     u32 *tab = (a.need && a.need[j]) ? a.arena + a.table_off[j] : nullptr;
     u32 *hist = GLOBAL ? tab : s_hist + (threadIdx.x & (R0 - 1));
     if (!GLOBAL)
-        for (u32 c = threadIdx.x; c < span * R0; c += THREADS) s_hist[c] = 0;
+        for (u32 c = threadIdx.x; c < max(span * R0, (span + 31u) & ~31u); c += THREADS) s_hist[c] = 0;   // whole 32-cell groups (swizzle)
     __syncthreads();   // the decoded family, R and the zeroed table are visible
     const u32 R = m.R;
 
     // packed path: all columns <= 4 states, index * mul fits 16-bit lanes.  The choice must not
     // depend on the slice, hence no R here: R > 1 implies cells * R <= 16383 (replica selection above).
     const bool packed = !GLOBAL && !RANGE && a.data2 != nullptr && m.small && m.k <= 6 && cells <= 16383u;
-    if (packed) {
+    // un-replicated table on the packed path: spread the banks.  (On the uint8 path the same swizzle changed
+    // nothing: diabetes-shaped classes 0 / 1 / 2 1.142 / 0.690 / 0.349 -> 1.145 / 0.682 / 0.358 ms; with 3 - 21
+    // states per column the low index bits are spread already.)
+    const bool swz = packed && R == 1 && a.swizzle && a.p2_vec == 4 && cells >= 64u;
+    if (packed && swz) {
+        count_rows_p2_k<THREADS, 4, true>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
+    } else if (packed) {
         if (a.p2_two && m.k <= 2) {
             if (m.k == 0) count_rows_p2_two<0, THREADS>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
             else if (m.k == 1) count_rows_p2_two<1, THREADS>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
@@ -1268,6 +1299,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     }
     __syncthreads();
     if (!GLOBAL && !RANGE && R > 1) compact_replicas<THREADS>(s_hist, cells, R);
+    if (!GLOBAL && !RANGE && swz) {   // back to cell order: a warp per 32-cell group, read all, then write
+        const u32 lane = threadIdx.x & 31u;
+        for (u32 g = threadIdx.x >> 5; g < (cells + 31u) >> 5; g += THREADS / 32) {
+            const u32 v = s_hist[g * 32u + (lane ^ (g & 31u))];
+            __syncwarp();
+            s_hist[g * 32u + lane] = v;
+        }
+        __syncthreads();
+    }
 
     const bool single = !GLOBAL && !RANGE && a.S == 1;   // the CTA's shared-memory table is the whole local table
     if (a.push && single) {   // row-sharded: straight from shared memory to the owner rank, no local HBM copy
