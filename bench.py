@@ -752,7 +752,12 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # roofline of the dominant kernel = the count-kernel class that took most of the step
-    kernels = ["k_count<256,false> (tables <= 2048 cells in shared memory, lane replicas for the small ones)",
+    # class 0 runs 512 threads x 96 KB when every column streams the 2-bit packed copy and the batch's class-0 tables average
+    # >= 256 cells (class0_shape in csrc/bicgpu.cu: the alarm-shaped candidates), else 256 threads x 24 / 48 KB
+    c0_wide = args.workload == "alarm" and not os.environ.get("BIC_CLASS0_THREADS") and not os.environ.get("BIC_CLASS0_WORDS") \
+        and os.environ.get("BIC_CLASS0_WIDE", "1") != "0"
+    kernels = [("k_count<512,false>" if c0_wide else "k_count<256,false>") +
+               " (class 0: tables <= 2048 cells in shared memory, lane replicas for all but the largest)",
                "k_count<512,false> (tables <= 12288 cells in shared memory)",
                "k_count<1024,false> (tables <= 49152 cells in shared memory, one CTA per SM)",
                "k_count<1024,false,true> (tables > 49152 cells: shared-memory sub-range passes; k_count<256,true> L2 atomics "
