@@ -423,6 +423,50 @@ def test_packed_path_ragged_rows(N, two, monkeypatch):
         assert_scores(s.score_families_csr(node, off, par, no_cache=True), C.score_families(codes, card, node, off, par))
 
 
+@pytest.mark.parametrize("N", [70_001, 1_100_003])
+def test_packed_path_offsets_replicas_swizzle(N, monkeypatch):
+    """The last stage of the packed path (csrc/count_kernels.cuh, p2_group): counter offsets by
+    integer dot product, with and without a high column group, and the 16-bit-lane fallback when
+    the four low columns have four states each (their product does not fit a byte weight); lane
+    replicas beyond cells * R = 16383 and the 512-thread x 96 KB class-0 shape (class0_shape);
+    the bank swizzle of un-replicated tables (few rows: every table; many rows: tables above the
+    replica reach and class 1).  Counts equal the oracle's; the knobs that turn each piece off and
+    the uint8 path give the same bits."""
+    monkeypatch.setenv("BIC_PACK2_MIN_ROWS", "1")
+    rng = np.random.default_rng(N)
+    card = np.array([4, 4, 4, 4, 4, 4, 3, 2, 4, 3, 2, 2], dtype=np.int32)
+    codes = np.stack([rng.integers(0, c, size=N) for c in card]).astype(np.uint8)
+    codes[4] = (codes[0] + codes[1] * (codes[2] > 1)) % 4                    # structure: skewed cells
+    codes[11] = (codes[3] > 0).astype(np.uint8) & codes[10]
+    fams = [(4, [0, 1, 2, 3]),          # low columns 4 x 4 x 4 x 4 = 256: 16-bit-lane fallback; 1024 cells
+            (5, [0, 1, 2, 3, 4]),       # the same with two high columns... one: 4096 cells, class 1, fallback
+            (6, [0, 1, 2, 3, 4, 5]),    # 12 288 cells, class 1, low product 192: dot product with a high group
+            (7, [0, 1, 2]),             # 128 cells, no high group: one IDP per row
+            (9, [0, 1, 6, 7]),          # 288 cells
+            (10, [0, 1, 2, 8]),         # 512 cells: 32 replicas only in the wide shape
+            (11, [0, 1, 2, 3, 6]),      # 1536 cells: 16 replicas only without the 16-bit cap
+            (11, [0, 1, 2, 3, 4]),      # 2048 cells: above the replica reach, swizzled
+            (8, [0, 1, 2, 3, 6, 7]),    # 6144 cells, class 1
+            (3, []), (2, [3])]
+    node, off, par = csr_of(fams)
+    want_tabs = [C.family_counts(codes, card, i, ps) for i, ps in fams]
+
+    def run():
+        with pkg.BicScorer(codes, card) as s:
+            tabs = s.count_families([f[0] for f in fams], [f[1] for f in fams])
+            for (i, ps), t, w in zip(fams, tabs, want_tabs):
+                assert np.array_equal(t, w), (N, i, ps)
+            return s.score_families_csr(node, off, par, no_cache=True)
+
+    base = run()
+    assert_scores(base, C.score_families(codes, card, node, off, par))
+    for knob in ("BIC_SWIZZLE=0", "BIC_CLASS0_WIDE=0", "BIC_NO_PACK2=1"):
+        k, v = knob.split("=")
+        monkeypatch.setenv(k, v)
+        assert np.array_equal(run(), base), knob
+        monkeypatch.delenv(k)
+
+
 def test_packed_and_byte_paths_agree(monkeypatch):
     N = 600_000
     adj, card, cpts = synth.make_network(12, 18, 3, [2, 3, 4], seed=41)
