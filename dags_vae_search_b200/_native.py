@@ -55,7 +55,7 @@ class CacheStats(ctypes.Structure):
 class PlanIn(ctypes.Structure):
     _fields_ = [("sm_count", ctypes.c_int32), ("N", ctypes.c_int64), ("n", ctypes.c_int32), ("max_cells", ctypes.c_int64),
                 ("tables_in_hbm", ctypes.c_int32), ("class_count", ctypes.c_int64 * 4), ("class_cells", ctypes.c_int64 * 4),
-                ("class_alg_bytes", ctypes.c_int64 * 4), ("all_packed", ctypes.c_int32), ("passes3", ctypes.c_int32)]
+                ("class_alg_bytes", ctypes.c_int64 * 4), ("all_packed", ctypes.c_int32), ("passes3", ctypes.c_int32), ("items3", ctypes.c_int32)]
 
 
 class PlanOut(ctypes.Structure):

@@ -154,6 +154,8 @@ struct bic_ctx {
         int p2_two = 0;                        // BIC_P2_TWO=1: packed path, families of <= 3 columns keep two 64-row groups in flight
                                                //   (experiment; pigs-shaped class-0 launch 1.033 -> 1.087 ms, 3 runs each: off)
         bool swizzle = true;                   // BIC_SWIZZLE=0: un-replicated shared-memory tables in plain cell order
+        bool list3 = true;                     // BIC_NO_LIST3=1: class-3 grid of njobs x (most passes) items per slice, surplus items empty
+        bool c3_u16 = false;                   // BIC_C3_U16=1: class-3 sub-ranges with 16-bit counters (half the passes; count_rows_r16)
         bool topsplit = true;                  // BIC_TOPSPLIT=0: class-3 sub-ranges always by cell index, every pass computes the full index of every row
         bool u8_narrow = false;                // BIC_U8_NARROW=1: uint8 path of classes 0 / 1 loads 8 bytes per thread per column (experiment)
         bool tma = false;                      // BIC_TMA=1: uint8 path of classes 0 / 1 stages its rows with TMA bulk copies (experiment)
@@ -180,6 +182,8 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_TMA")) tma = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_NARROW")) u8_narrow = atoi(e) != 0;
             if (const char *e = getenv("BIC_TOPSPLIT")) topsplit = atoi(e) != 0;
+            if (const char *e = getenv("BIC_C3_U16")) c3_u16 = atoi(e) != 0;
+            if (const char *e = getenv("BIC_NO_LIST3")) list3 = atoi(e) == 0;
             if (const char *e = getenv("BIC_SWIZZLE")) swizzle = atoi(e) != 0;
             if (const char *e = getenv("BIC_P2_TWO")) p2_two = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_TWO")) { int v = atoi(e); u8_two = v <= 1 ? 0 : v >= 3 ? 3 : 2; }
@@ -217,7 +221,7 @@ struct bic_ctx {
     u32 **d_peer = nullptr;              // device array [world] of exchange-buffer pointers (own buffer at [rank])
     int xchg_state = 0;                  // 0 not tried, 1 ready, -1 unavailable (fall back to ncclAllReduce of the tables)
     int *d_barrier = nullptr;            // 4 bytes all-reduced as the "all pushes have landed" barrier
-    DevBuf terms, gkeys, gbad, cellbuf, meta, jobs_sorted;  // staged family terms (one all-reduce), all-gathered keys / reject flags, parked cell indices (class 3)
+    DevBuf terms, gkeys, gbad, cellbuf, meta, jobs_sorted, items3;  // staged family terms (one all-reduce), all-gathered keys / reject flags, parked cell indices (class 3)
     cudaEvent_t ev_wait = nullptr;       // bic_wait_stream
     bool fast_ok = true;     // small warm batches: try k_score_small first (off after a miss, on again after an all-hit call)
 };
@@ -403,14 +407,19 @@ int refresh_ntotal(bic_ctx *c) {
 // cells) 512 threads sharing 96 KB (32 replicas up to 768 cells, 16 up to 1536; still 1024 threads
 // per SM) cut the class-0 launch from 51.5 to 45.2 ms: by then the shared-memory data pipe was the
 // limiter (91 %, half of its atomic wavefronts bank conflicts).  Tiny tables (pigs-shaped: <= 81
-// cells) already run with 32 replicas and keep the small CTAs.
+// cells) already run with 32 replicas and keep the small CTAs, and so do datasets of fewer than 2^20
+// rows (sachs, 5000 rows: 0.085 -> 0.136 ms per class-0 launch with the wide shape).
+// On the uint8 path (its 16-bit lanes keep the cells * R <= 16383 cap, and the in-flight rows need the L1) the
+// same move is worth less: diabetes-shaped class-0 launch 1.135 ms at 256 x 24 KB, 1.094 / 1.080 / 1.109 ms at
+// 512 x 48 / 64 / 96 KB, 1.57 ms at 1024 threads.  512 x 64 KB it is.
 constexpr u32 CLASS0_WORDS_WIDE = 24576;
-void class0_shape(bool all_packed, long long count0, long long cells0, const bic_ctx::Tuning &tune, int &threads, u32 &words) {
+constexpr u32 CLASS0_WORDS_WIDE_U8 = 16384;
+void class0_shape(bool all_packed, long long N, long long count0, long long cells0, const bic_ctx::Tuning &tune, int &threads, u32 &words) {
     threads = tune.class0_threads;
     words = all_packed ? tune.class0_words_packed : tune.class0_words;
-    if (all_packed && !tune.class0_explicit && tune.class0_wide && count0 > 0 && cells0 >= 256 * count0) {
+    if (!tune.class0_explicit && tune.class0_wide && N >= (1ll << 20) && count0 > 0 && cells0 >= 256 * count0) {
         threads = 512;
-        words = CLASS0_WORDS_WIDE;
+        words = all_packed ? CLASS0_WORDS_WIDE : CLASS0_WORDS_WIDE_U8;
     }
 }
 
@@ -419,13 +428,13 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
     // measured on B200 (profiles/): streaming loads, L2 atomics, rows per second one CTA counts, CTA set-up
     const double HBM_BPS = 6.0e12, RED_PER_S = 1.0e11, CTA_ROWS_PER_S = 5.0e9, CTA_SETUP_S = 4.0e-6;
     int c0t; u32 c0w;
-    class0_shape(in.all_packed != 0, in.class_count[0], in.class_cells[0], tune, c0t, c0w);
+    class0_shape(in.all_packed != 0, in.N, in.class_count[0], in.class_cells[0], tune, c0t, c0w);
     const long long resident[NCLASS] = {1024 / c0t, 2, 1, 4};   // CTAs of a class one SM holds (64 registers per thread; 192 KB tables)
     // class 3 in passes over shared-memory sub-ranges (k_count<1024, false, true>) when every table
     // of the launch fits range_passes sub-ranges and a slice holds at least 4 rows per cell
     const long long span = CLASS2_CELLS;
     const int P3gen = (int)((in.max_cells + span - 1) / span);
-    const int P3 = std::max(P3gen, (int)in.passes3);   // top split (range_plan) never needs more passes than the generic cut today
+    const int P3 = in.passes3 > 0 ? (int)in.passes3 : P3gen;   // top split: as many as the generic cut; 16-bit counters: about half
     // One pass over a thread-block cluster whose CTAs share the table (k_count_cluster) when it fits
     // 8 x 192 KB of distributed shared memory; else sub-range passes; else (few rows) L2 atomics.
     int CL = 0;
@@ -448,7 +457,7 @@ void plan_count(const bic_plan_in_t &in, const bic_ctx::Tuning &tune, bic_plan_o
             // three rounds, not two.
             const bool clu3 = k == 3 && CL > 0;
             const bool rng3 = k == 3 && (ranged || clu3);   // one CTA per SM, rows >> cells
-            const long long ctas = cnt * (clu3 ? CL : rng3 ? P3 : 1);
+            const long long ctas = (rng3 && !clu3 && in.items3 > 0) ? (long long)in.items3 : cnt * (clu3 ? CL : rng3 ? P3 : 1);
             const long long slots = (long long)in.sm_count * (rng3 ? 1 : resident[k]);
             const long long hi = std::min(rng3 ? std::min(smax, in.N / (4ll * in.max_cells)) : smax,
                                           std::max<long long>(1, 4 * slots / ctas));
@@ -616,7 +625,11 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     na.all = all_tables ? 1 : 0;
     bic_plan_in_t pin;
     pin.sm_count = c->sm_count; pin.N = c->N; pin.n = c->n; pin.max_cells = h.max_cells; pin.tables_in_hbm = all_tables ? 1 : 0; pin.all_packed = c->all_packed ? 1 : 0;
-    pin.passes3 = (c->tune.topsplit && !c->tune.park_cells) ? (int)h.max_passes3 : 0;
+    const bool c3_u16 = c->tune.c3_u16 && !c->tune.park_cells;
+    // class 3 in passes: one work item per (family, pass it needs) when the decoded families are parked (k_range_items)
+    const bool list3 = c->tune.park_meta && njobs <= (1ll << 22) && !c->tune.park_cells && c->tune.list3;
+    pin.items3 = list3 ? (int)(c3_u16 ? h.sum_passes3_u16 : h.sum_passes3) : 0;
+    pin.passes3 = c3_u16 ? (int)h.max_passes3_u16 : (c->tune.topsplit && !c->tune.park_cells) ? (int)h.max_passes3 : 0;
     for (int k = 0; k < NCLASS; ++k) {
         pin.class_count[k] = h.class_count[k];
         pin.class_cells[k] = (long long)h.class_cells[k];
@@ -665,6 +678,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
     a.tma = c->tune.tma ? 1 : 0;
     a.u8_narrow = c->tune.u8_narrow ? 1 : 0;
     a.swizzle = c->tune.swizzle ? 1 : 0;
+    a.c3_u16 = c3_u16 ? 1 : 0;
     a.topsplit = (c->tune.topsplit && !c->tune.park_cells) ? 1 : 0;   // the parked cell indices follow the generic cut
     a.u8_two = c->tune.u8_two;
     a.p2_two = c->tune.p2_two;
@@ -704,6 +718,16 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         a.P = (k == 3 && ranged) ? P3 : 1;   // launch-wide: the family with the most sub-ranges
         a.span = span;
         long long items = cnt * a.S * a.P;
+        a.items3 = nullptr;
+        a.nitems3 = 0;
+        if (k == 3 && ranged && CL == 0 && list3 && a.meta && pin.items3 > 0) {
+            CU(c->items3.ensure((size_t)pin.items3 * sizeof(int2)));
+            k_range_items<<<1, 1024, 0, c->stream>>>(a.jobs, (int)cnt, a.meta, span, a.c3_u16, a.topsplit, c->items3.as<int2>(), (u32)pin.items3); LAUNCH(c);
+            CU(cudaGetLastError());
+            a.items3 = c->items3.as<int2>();
+            a.nitems3 = pin.items3;
+            items = (long long)pin.items3 * a.S;
+        }
         if (items * (clustered ? CL : 1) > 0x7fffffffLL) return fail(c, BIC_ERR_ARG, "too many count work items in one launch");
         bic_ctx::EvPair ev = {nullptr, nullptr, k};
         if (c->prof_on) {   // CUDA events on the launching stream, one pair per count launch
@@ -720,7 +744,7 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         // shared memory per CTA: class 0 gets several times its largest table so that small tables
         // run with 32 or 16 bank-interleaved lane replicas (conflict-free atomics).
         int c0t; u32 c0w;
-        class0_shape(c->all_packed, (long long)h.class_count[0], (long long)h.class_cells[0], c->tune, c0t, c0w);
+        class0_shape(c->all_packed, c->N, (long long)h.class_count[0], (long long)h.class_cells[0], c->tune, c0t, c0w);
         const u32 cap[NCLASS] = {c0w, CLASS1_CELLS, CLASS2_CELLS, 0};
         a.cap_words = cap[k];
         const u32 GLOBAL_STAGE = 8192;   // class 3 straight into HBM: shared memory only stages the final reduce
@@ -1189,7 +1213,7 @@ int bic_destroy(bic_ctx *c) {
     DevBuf *bufs[] = {&c->keybuf, &c->inst, &c->flag, &c->rank, &c->bsum32, &c->bsum64, &c->cells_arr, &c->class_jobs,
                       &c->need, &c->table_off, &c->done, &c->arena, &c->dag_bad, &c->in_stage, &c->in_stage2,
                       &c->in_stage3, &c->in_stage4, &c->out_stage, &c->tmp_ll, &c->donor, &c->donor_best,
-                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad, &c->cellbuf, &c->meta, &c->jobs_sorted};
+                      &c->derived_list, &c->derived_sorted, &c->owner, &c->xoff, &c->fp_buf, &c->terms, &c->gkeys, &c->gbad, &c->cellbuf, &c->meta, &c->jobs_sorted, &c->items3};
     for (DevBuf *b : bufs) b->release();
     if (c->data) cudaFree(c->data);
     if (c->data2) cudaFree(c->data2);

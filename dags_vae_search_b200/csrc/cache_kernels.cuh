@@ -436,7 +436,14 @@ __device__ __forceinline__ void describe_family(const u64 *key, int W64, const i
     atomicAdd(&hdr->alg_bytes[cls], (u64)(k + 1) * (u64)N + 4ull * cells);
     atomicAdd(&hdr->class_cells[cls], cells);
     atomicMax(&hdr->max_cells, (u32)cells);
-    if (cls == 3) atomicMax(&hdr->max_passes3, range_plan((u32)cells, k, rad0, CLASS2_CELLS, true).passes);
+    if (cls == 3) {
+        const u32 p32 = range_plan((u32)cells, k, rad0, CLASS2_CELLS, true).passes;
+        const u32 p16 = range_plan((u32)cells, k, rad0, k <= 6 ? 2u * CLASS2_CELLS : CLASS2_CELLS, false).passes;
+        atomicMax(&hdr->max_passes3, p32);
+        atomicMax(&hdr->max_passes3_u16, p16);
+        atomicAdd(&hdr->sum_passes3, p32);
+        atomicAdd(&hdr->sum_passes3_u16, p16);
+    }
 }
 
 // Owners of PENDING entries take id = base + rank, publish their key in the registry and

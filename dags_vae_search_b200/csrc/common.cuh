@@ -45,6 +45,8 @@ struct Header {
     u32 lvl_cursor[DERIVE_LEVELS];  // device scratch: fill positions while the derived families are grouped by level
     u64 owned_max;             // row-sharded runs: most cells any one rank owns (must fit a slot of the exchange buffer)
     u32 max_passes3;           // most sub-range passes any class-3 family of the sub-batch needs (range_plan)
+    u32 max_passes3_u16;       // the same with 16-bit counters (sub-ranges of twice the cells; k <= 6 only)
+    u32 sum_passes3, sum_passes3_u16;   // sub-range passes of all class-3 families together: work items per row slice (k_range_items)
 };
 
 // How a class-3 family (table above one CTA's shared memory) is cut into sub-ranges that a CTA counts

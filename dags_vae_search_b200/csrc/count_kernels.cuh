@@ -45,6 +45,10 @@ struct CountArgs {
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int swizzle;             // packed path, un-replicated tables: bank swizzle of the cell index (swz_off)
+    const int2 *items3;      // RANGE kernel: (job, pass) per work item of a row slice (k_range_items), or NULL: njobs * P items
+    int nitems3;
+    int c3_u16;              // RANGE kernel: 16-bit counters, two per word (sub-ranges of 2 * span cells: half the passes), spilled
+                             //   into the HBM table between barrier-separated phases so that none can overflow (count_rows_r16)
     int topsplit;            // RANGE kernel: sub-ranges along the first parent's states where range_plan() allows it
     int u8_narrow;           // uint8 path of classes 0 / 1: 8-byte loads (experiment)
     int p2_two;              // packed path, families of <= 3 columns: two 64-row groups in flight per thread (datasets beyond L2)
@@ -135,6 +139,46 @@ __global__ void k_decode_jobs(const u64 *__restrict__ keys, long long key_base, 
     }
     c.pad[0] = c.pad[1] = 0;
     out[j] = c;
+}
+
+// Work items of the class-3 sub-range kernel.  The grid used to hold njobs x P items per row slice, P the
+// pass count of the largest table of the launch; families with smaller tables left their surplus items
+// empty, and with one CTA per SM an empty item is an idle SM (ncu on the diabetes-shaped step: SMs active
+// half of the launch).  This lists (job, pass) for exactly the passes every family needs; the host sizes the
+// row slices for that number of items.  One block; `cnt` = class-3 jobs of the launch.
+__global__ void __launch_bounds__(1024) k_range_items(const int *__restrict__ jobs, int cnt, const FamMetaC *__restrict__ meta, u32 span,
+                                                      int u16, int topsplit, int2 *items, u32 cap) {
+    __shared__ u32 s_scan[1024];
+    __shared__ u32 s_carry;
+    const int tid = (int)threadIdx.x;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < cnt; base += 1024) {
+        const int i = base + tid;
+        u32 p = 0;
+        int job = -1;
+        if (i < cnt) {
+            job = jobs[i];
+            const int kk = meta[job].k;
+            const u32 rad0 = kk > 0 ? (u32)meta[job].rad[0] : 1u;
+            p = (u16 && kk <= 6) ? range_plan(meta[job].cells, kk, rad0, 2u * span, false).passes
+                                 : range_plan(meta[job].cells, kk, rad0, span, topsplit != 0).passes;
+        }
+        s_scan[tid] = p;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const u32 x = tid >= o ? s_scan[tid - o] : 0u;
+            __syncthreads();
+            s_scan[tid] += x;
+            __syncthreads();
+        }
+        const u32 first = s_carry + s_scan[tid] - p;
+        for (u32 q = 0; q < p; ++q)
+            if (first + q < cap) items[first + q] = make_int2(job, (int)q);
+        __syncthreads();
+        if (tid == 1023) s_carry += s_scan[1023];
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -384,6 +428,66 @@ __device__ __forceinline__ void count_rows_top(const FamMeta &m, const uint8_t *
                 const u32 d = __byte_perm(ts[i], 0u, 0x4440u + b) - s0;
                 if (4 * i + b < nv && d < ns) bump_off<false>(hist, d * low4 + off[4 * i + b]);
             }
+    }
+}
+
+// Class 3 with 16-bit counters (BIC_C3_U16): a sub-range holds 2 * H cells (H = the CTA's words), cell d
+// of the sub-range in word d mod H, low half for d < H and high half above - neighbouring cells stay in
+// neighbouring banks - so a table needs half the passes over the rows.  No counter can overflow: the
+// row loop runs in phases of at most 48 K rows per CTA, and between two phases (block-wide barriers)
+// every half that has reached 16 384 is added to the HBM table and cleared; 16 383 + 49 152 = 65 535.
+template <int K, int THREADS>
+__device__ __forceinline__ void count_rows_r16(const FamMeta &m, const uint8_t *__restrict__ data, long long stride,
+                                               long long N, long long v0, long long v1, u32 *hist, u32 lo, u32 span,
+                                               u32 H, u32 *__restrict__ tab) {
+    constexpr int PH = 49152 / (16 * THREADS);   // 16-row groups per thread and phase
+    static_assert(PH >= 1, "a phase adds at most 49152 rows");
+    const uint8_t *cp[K + 1];
+    u32 rad[K + 1];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        cp[a] = data + (long long)m.par[a] * stride;
+        rad[a] = m.rad[a];
+    }
+    cp[K] = data + (long long)m.node * stride;
+    rad[K] = (u32)m.r;
+    for (long long base = v0; base < v1; base += (long long)PH * THREADS) {
+#pragma unroll 1
+        for (int i = 0; i < PH; ++i) {
+            const long long v = base + (long long)i * THREADS + threadIdx.x;
+            if (v >= v1) break;
+            uint4 w[K + 1];
+#pragma unroll
+            for (int a = 0; a <= K; ++a) w[a] = ld_stream_v4(cp[a] + v * 16);
+            u32 idx[16];
+            cells_u32<K>(w, rad, 1u, idx);
+            const int nv = v * 16 + 16 <= N ? 16 : (int)(N - v * 16);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const u32 d = idx[b] - lo;
+                if (b < nv && d < span) {
+                    const bool up = d >= H;
+                    atomicAdd(hist + (up ? d - H : d), up ? 0x10000u : 1u);
+                }
+            }
+        }
+        if (base + (long long)PH * THREADS < v1) {   // uniform: another phase follows
+            __syncthreads();
+            for (u32 c = threadIdx.x * 4u; c < H; c += THREADS * 4u) {   // H is a multiple of 4
+                uint4 q = *reinterpret_cast<const uint4 *>(hist + c);
+                if ((q.x | q.y | q.z | q.w) & 0xC000C000u) {
+                    u32 qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const u32 l16 = qs[e] & 0xffffu, h16 = qs[e] >> 16;
+                        if (l16 >= 0x4000u) { atomicAdd(tab + lo + c + e, l16); qs[e] &= 0xffff0000u; }
+                        if (h16 >= 0x4000u) { atomicAdd(tab + lo + H + c + e, h16); qs[e] &= 0x0000ffffu; }
+                    }
+                    *reinterpret_cast<uint4 *>(hist + c) = make_uint4(qs[0], qs[1], qs[2], qs[3]);
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -1159,11 +1263,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
 
     // slice-major item order: the CTAs resident at any moment work on the same row window of
     // the dataset, which the host sizes to stay L2-resident
-    const int per_slice = RANGE ? a.njobs * a.P : a.njobs;
+    const bool listed = RANGE && a.items3 != nullptr;
+    const int per_slice = RANGE ? (listed ? a.nitems3 : a.njobs * a.P) : a.njobs;
     const int slice = blockIdx.x / per_slice;
     const int in_slice = blockIdx.x - slice * per_slice;
-    const int pass = RANGE ? in_slice / a.njobs : 0;
-    const int j = a.jobs[in_slice - pass * a.njobs];
+    int pass = 0, j;
+    if (listed) {
+        const int2 it = a.items3[in_slice];
+        j = it.x;
+        pass = it.y;
+    } else {
+        pass = RANGE ? in_slice / a.njobs : 0;
+        j = a.jobs[in_slice - pass * a.njobs];
+    }
     if (a.meta) {   // one coalesced 128-byte read of the parked record
         if (threadIdx.x < 8) reinterpret_cast<uint4 *>(&s_c)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.meta + j) + threadIdx.x);
     } else if (threadIdx.x == 0) {
@@ -1179,7 +1291,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     if (RANGE) {
         const int kk = a.meta ? s_c.k : m.k;
         const u32 rad0 = kk > 0 ? (a.meta ? (u32)s_c.rad[0] : m.rad[0]) : 1u;
-        rp = range_plan(cells, kk, rad0, a.span, a.topsplit != 0);
+        if (a.c3_u16 && kk <= 6) rp = range_plan(cells, kk, rad0, 2u * a.span, false);   // two 16-bit counters per word
+        else rp = range_plan(cells, kk, rad0, a.span, a.topsplit != 0);
         low = rp.ns ? cells / rad0 : 0u;
     }
     const u32 lo = RANGE ? (u32)pass * rp.span : 0u;
@@ -1232,7 +1345,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     u32 *tab = (a.need && a.need[j]) ? a.arena + a.table_off[j] : nullptr;
     u32 *hist = GLOBAL ? tab : s_hist + (threadIdx.x & (R0 - 1));
     if (!GLOBAL)
-        for (u32 c = threadIdx.x; c < max(span * R0, (span + 31u) & ~31u); c += THREADS) s_hist[c] = 0;   // whole 32-cell groups (swizzle)
+        for (u32 c = threadIdx.x; c < ((RANGE && a.c3_u16) ? a.span : max(span * R0, (span + 31u) & ~31u)); c += THREADS)
+            s_hist[c] = 0;   // whole 32-cell groups (swizzle); 16-bit mode: all a.span words
     __syncthreads();   // the decoded family, R and the zeroed table are visible
     const u32 R = m.R;
 
@@ -1255,6 +1369,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
         else count_rows_p2_k<THREADS, 1>(m, a.data2, a.stride2, a.N, b0, b1, hist, a.k30, a.k28, a.k26);
     } else if (RANGE && a.cellbuf) {
         count_rows_cells<THREADS>(a.cellbuf + (size_t)(in_slice - pass * a.njobs) * (size_t)a.stride, a.N, v0, v1, hist, lo, span);
+    } else if (RANGE && a.c3_u16 && m.k <= 6) {
+        switch (m.k) {
+            case 0: count_rows_r16<0, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+            case 1: count_rows_r16<1, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+            case 2: count_rows_r16<2, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+            case 3: count_rows_r16<3, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+            case 4: count_rows_r16<4, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+            case 5: count_rows_r16<5, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+            default: count_rows_r16<6, THREADS>(m, a.data, a.stride, a.N, v0, v1, hist, lo, span, a.span, tab); break;
+        }
     } else if (RANGE && rp.ns) {
         const u32 s0 = (u32)pass * rp.ns, nsh = span / low;   // the last pass may hold fewer states
         switch (m.k) {
@@ -1314,7 +1438,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
         push_table<THREADS, true>(a, j, s_hist, cells);
         return;
     }
-    if (!GLOBAL && tab) {   // merge this slice's shared-memory table into the HBM table
+    if (RANGE && a.c3_u16 && m.k <= 6) {   // what the phases left in the 16-bit halves
+        for (u32 c = threadIdx.x; c < a.span; c += THREADS) {
+            const u32 v = s_hist[c], l16 = v & 0xffffu, h16 = v >> 16;
+            if (l16) atomicAdd(tab + lo + c, l16);
+            if (h16) atomicAdd(tab + lo + a.span + c, h16);
+        }
+    } else if (!GLOBAL && tab) {   // merge this slice's shared-memory table into the HBM table
         for (u32 c = threadIdx.x; c < span; c += THREADS) {
             u32 v = s_hist[c];
             if (v) atomicAdd(tab + lo + c, v);

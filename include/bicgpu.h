@@ -225,6 +225,8 @@ typedef struct {
     int32_t passes3;           /* most sub-range passes a class-3 family of the batch needs      *
                                 * (sub-ranges may follow the first parent's states);            *
                                 * 0: ceil(max_cells / 49152)                                    */
+    int32_t items3;            /* class-3 work items per row slice (sum of the families' passes); *
+                                * 0: class_count[3] * passes                                    */
 } bic_plan_in_t;
 typedef struct {
     int32_t slices[4];         /* row slices per family, per class                              */

@@ -535,6 +535,9 @@ def test_class3_cluster_passes_and_l2_atomics_match_oracle(monkeypatch):
     monkeypatch.delenv("BIC_CLUSTER")
     monkeypatch.setenv("BIC_RANGE_PASSES", "0")
     assert np.array_equal(run(), ranged)                      # L2 atomics
+    monkeypatch.delenv("BIC_RANGE_PASSES")
+    monkeypatch.setenv("BIC_C3_U16", "1")
+    assert np.array_equal(run(), ranged)                      # 16-bit counters: half the passes, spills between phases
 
 
 def test_class3_top_split_matches_generic_cut(monkeypatch):
@@ -579,6 +582,10 @@ def test_class3_top_split_matches_generic_cut(monkeypatch):
     monkeypatch.delenv("BIC_TOPSPLIT")
     monkeypatch.setenv("BIC_CLASS2_THREADS", "512")          # k_count<512, false, true>
     assert np.array_equal(run(), split)
+    monkeypatch.setenv("BIC_C3_U16", "1")                    # 16-bit counters, phase spills (count_rows_r16), 512 threads
+    assert np.array_equal(run(), split)
+    monkeypatch.delenv("BIC_CLASS2_THREADS")
+    assert np.array_equal(run(), split)                      # ... and 1024 threads
 
 
 def test_slice_choice_does_not_change_bits(monkeypatch):

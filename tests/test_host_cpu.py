@@ -278,8 +278,11 @@ def test_launch_plan_rules(monkeypatch):
     assert packed["slices"][0] == windows(37, N, 128)
     assert all(1 <= s <= N // 65536 for s in alarm["slices"])
     # a handful of families of a search step: enough slices to occupy the GPU, well below the window count of a full pass
+    # (tables averaging >= 256 cells run 512-thread class-0 CTAs, two per SM; small tables 256-thread CTAs, four per SM)
     few = nat.plan_slices(N, 37, [(5, 700)] * 40)
-    assert 148 * 4 // 40 <= few["slices"][0] <= 4 * 148 * 4 // 40
+    assert 148 * 2 // 40 <= few["slices"][0] <= 4 * 148 * 2 // 40
+    few_small = nat.plan_slices(N, 37, [(3, 81)] * 40)
+    assert 148 * 4 // 40 <= few_small["slices"][0] <= 4 * 148 * 4 // 40
 
     # diabetes-shaped local moves (5.2 GB of rows): the few large-table families are not cut into
     # 162 L2 windows (their merges would cost more than the counting); class 3 (194 481 cells) runs
