@@ -752,10 +752,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # roofline of the dominant kernel = the count-kernel class that took most of the step
-    # class 0 runs 512 threads x 96 KB when every column streams the 2-bit packed copy and the batch's class-0 tables average
-    # >= 256 cells (class0_shape in csrc/bicgpu.cu: the alarm-shaped candidates), else 256 threads x 24 / 48 KB
-    c0_wide = args.workload == "alarm" and not os.environ.get("BIC_CLASS0_THREADS") and not os.environ.get("BIC_CLASS0_WORDS") \
-        and os.environ.get("BIC_CLASS0_WIDE", "1") != "0"
+    # class 0 runs 512 threads x 96 KB (all columns packed) or x 64 KB (uint8 path) when the batch's class-0 tables average
+    # >= 256 cells on >= 2^20 rows (class0_shape in csrc/bicgpu.cu: the alarm- and diabetes-shaped steps), else 256 threads
+    # x 24 / 48 KB
+    c0_wide = args.workload in ("alarm", "diabetes") and not os.environ.get("BIC_CLASS0_THREADS") and not os.environ.get("BIC_CLASS0_WORDS") \
+        and os.environ.get("BIC_CLASS0_WIDE", "1") != "0" and rows >= (1 << 20)
     kernels = [("k_count<512,false>" if c0_wide else "k_count<256,false>") +
                " (class 0: tables <= 2048 cells in shared memory, lane replicas for all but the largest)",
                "k_count<512,false> (tables <= 12288 cells in shared memory)",
