@@ -154,6 +154,9 @@ struct bic_ctx {
         int p2_two = 0;                        // BIC_P2_TWO=1: packed path, families of <= 3 columns keep two 64-row groups in flight
                                                //   (experiment; pigs-shaped class-0 launch 1.033 -> 1.087 ms, 3 runs each: off)
         bool swizzle = true;                   // BIC_SWIZZLE=0: un-replicated shared-memory tables in plain cell order
+        u32 tier0 = 768, tier1 = 3072;         // BIC_TIER0 / BIC_TIER1: cell limits of the first launch over the class-0 / class-1 list (0: one launch).
+                                               //   Alarm-shaped step 54.45 ms untiered; 53.05 (768, 0); 53.58 (0, 3072); 52.23 (768, 3072); 52.37 (1024, 3072);
+                                               //   52.71 (1536, 3072)
         bool list3 = true;                     // BIC_NO_LIST3=1: class-3 grid of njobs x (most passes) items per slice, surplus items empty
         bool c3_u16 = false;                   // BIC_C3_U16=1: class-3 sub-ranges with 16-bit counters (half the passes; count_rows_r16)
         bool topsplit = true;                  // BIC_TOPSPLIT=0: class-3 sub-ranges always by cell index, every pass computes the full index of every row
@@ -184,6 +187,8 @@ struct bic_ctx {
             if (const char *e = getenv("BIC_TOPSPLIT")) topsplit = atoi(e) != 0;
             if (const char *e = getenv("BIC_C3_U16")) c3_u16 = atoi(e) != 0;
             if (const char *e = getenv("BIC_NO_LIST3")) list3 = atoi(e) == 0;
+            if (const char *e = getenv("BIC_TIER0")) { int v = atoi(e); if (v >= 0 && v < (int)CLASS0_CELLS) tier0 = (u32)v; }
+            if (const char *e = getenv("BIC_TIER1")) { int v = atoi(e); if (v >= 0 && v <= 3072) tier1 = (u32)v; }
             if (const char *e = getenv("BIC_SWIZZLE")) swizzle = atoi(e) != 0;
             if (const char *e = getenv("BIC_P2_TWO")) p2_two = atoi(e) != 0;
             if (const char *e = getenv("BIC_U8_TWO")) { int v = atoi(e); u8_two = v <= 1 ? 0 : v >= 3 ? 3 : 2; }
@@ -763,13 +768,37 @@ int run_count(bic_ctx *c, const u64 *keys, long long key_base, long long njobs, 
         }
         a.stage_words = k == 3 ? (clustered ? clwords : ranged ? span : GLOBAL_STAGE) : cap[k];
         const size_t ring256 = a.tma ? tma_ring_bytes(256) : 0, ring512 = a.tma ? tma_ring_bytes(512) : 0;   // TMA staging ring behind the table
+        // Tiers (all-packed datasets in the wide class-0 shape): the tables above the replica reach of a 96 KB CTA
+        // are counted by a second launch over the same class list with 1024 threads x 192 KB (32 replicas up to
+        // 1536 cells, 16 up to 3072); a CTA whose family belongs to the other launch returns at once.
+        const bool tiers = c->all_packed && c0t == 512 && c0w == CLASS0_WORDS_WIDE && !a.tma && (c->tune.tier0 || c->tune.tier1);
+        a.tier_lo = a.tier_hi = 0;
+        if (k == 0 && tiers && c->tune.tier0) {
+            a.tier_lo = 0; a.tier_hi = c->tune.tier0;
+            TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32))));
+            a.tier_lo = c->tune.tier0 + 1; a.tier_hi = 0xffffffffu;
+            a.cap_words = a.stage_words = CLASS2_CELLS;
+            TRY((launch_count<1024, false>(c, a, items, CLASS2_CELLS * sizeof(u32))));
+            a.tier_lo = a.tier_hi = 0;
+        } else {
         if (k == 0 && c0t == 256) TRY((launch_count<256, false>(c, a, items, cap[0] * sizeof(u32) + ring256)));
         if (k == 0 && c0t == 512) TRY((launch_count<512, false>(c, a, items, cap[0] * sizeof(u32) + ring512)));
         if (k == 0 && c0t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[0] * sizeof(u32))));
+        }
         const int c1t = c->tune.class1_threads;
+        if (k == 1 && tiers && c->tune.tier1) {
+            a.tier_lo = 0; a.tier_hi = c->tune.tier1;
+            a.cap_words = a.stage_words = CLASS2_CELLS;
+            TRY((launch_count<1024, false>(c, a, items, CLASS2_CELLS * sizeof(u32))));
+            a.tier_lo = c->tune.tier1 + 1; a.tier_hi = 0xffffffffu;
+            a.cap_words = a.stage_words = cap[1];
+            TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32))));
+            a.tier_lo = a.tier_hi = 0;
+        } else {
         if (k == 1 && c1t == 256) TRY((launch_count<256, false>(c, a, items, cap[1] * sizeof(u32) + ring256)));
         if (k == 1 && c1t == 512) TRY((launch_count<512, false>(c, a, items, cap[1] * sizeof(u32) + ring512)));
         if (k == 1 && c1t == 1024) TRY((launch_count<1024, false>(c, a, items, cap[1] * sizeof(u32))));
+        }
         const bool wide = c->tune.class2_threads == 1024;
         if (k == 2 && !wide) TRY((launch_count<512, false>(c, a, items, cap[2] * sizeof(u32))));
         if (k == 2 && wide) TRY((launch_count<1024, false>(c, a, items, cap[2] * sizeof(u32))));

@@ -45,6 +45,8 @@ struct CountArgs {
     const int *donor;        // per job: job whose table this one is marginalised from, or -1 (nullable)
     u32 *cellbuf;            // RANGE kernel: cell index of every row, [position in the class-3 job list][stride] (k_cells), or NULL
     int swizzle;             // packed path, un-replicated tables: bank swizzle of the cell index (swz_off)
+    u32 tier_lo, tier_hi;    // the launch counts only the families with tier_lo <= cells <= tier_hi (0 / 0: all): one class list,
+                             //   two launches with different CTA shapes (run_count)
     const int2 *items3;      // RANGE kernel: (job, pass) per work item of a row slice (k_range_items), or NULL: njobs * P items
     int nitems3;
     int c3_u16;              // RANGE kernel: 16-bit counters, two per word (sub-ranges of 2 * span cells: half the passes), spilled
@@ -1284,6 +1286,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? BIC_C0_MINBLOCKS : T
     __syncthreads();
 
     const u32 cells = a.meta ? s_c.cells : m.cells;
+    if (a.tier_hi && (cells < a.tier_lo || cells > a.tier_hi)) return;   // the other launch over this class list counts the family
     // RANGE: this family's sub-ranges (generic cut, or runs of states of the first parent)
     RangePlan rp;
     rp.span = a.span; rp.passes = 1; rp.ns = 0;
