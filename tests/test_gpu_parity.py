@@ -430,8 +430,9 @@ def test_packed_path_offsets_replicas_swizzle(N, monkeypatch):
     the four low columns have four states each (their product does not fit a byte weight); lane
     replicas beyond cells * R = 16383 and the 512-thread x 96 KB class-0 shape (class0_shape);
     the bank swizzle of un-replicated tables (few rows: every table; many rows: tables above the
-    replica reach and class 1).  Counts equal the oracle's; the knobs that turn each piece off and
-    the uint8 path give the same bits."""
+    replica reach and class 1); the class-0 / class-1 lists counted by two launches with different
+    CTA shapes (tiers).  Counts equal the oracle's; the knobs that turn each piece off and the uint8
+    path give the same bits."""
     monkeypatch.setenv("BIC_PACK2_MIN_ROWS", "1")
     rng = np.random.default_rng(N)
     card = np.array([4, 4, 4, 4, 4, 4, 3, 2, 4, 3, 2, 2], dtype=np.int32)
@@ -460,7 +461,8 @@ def test_packed_path_offsets_replicas_swizzle(N, monkeypatch):
 
     base = run()
     assert_scores(base, C.score_families(codes, card, node, off, par))
-    for knob in ("BIC_SWIZZLE=0", "BIC_CLASS0_WIDE=0", "BIC_NO_PACK2=1"):
+    # BIC_TIER0 / BIC_TIER1 = 0: one launch per class list instead of two with different CTA shapes
+    for knob in ("BIC_SWIZZLE=0", "BIC_CLASS0_WIDE=0", "BIC_TIER0=0", "BIC_TIER1=0", "BIC_NO_PACK2=1"):
         k, v = knob.split("=")
         monkeypatch.setenv(k, v)
         assert np.array_equal(run(), base), knob
