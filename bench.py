@@ -757,9 +757,14 @@ def main():
     # x 24 / 48 KB
     c0_wide = args.workload in ("alarm", "diabetes") and not os.environ.get("BIC_CLASS0_THREADS") and not os.environ.get("BIC_CLASS0_WORDS") \
         and os.environ.get("BIC_CLASS0_WIDE", "1") != "0" and rows >= (1 << 20)
-    kernels = [("k_count<512,false>" if c0_wide else "k_count<256,false>") +
+    # all-packed datasets in the wide shape count the class-0 / class-1 lists in two launches each (tiers, BIC_TIER0 / BIC_TIER1):
+    # tables above the 96 KB replica reach go to 1024 threads x 192 KB; the class time covers both launches
+    tiered = c0_wide and args.workload == "alarm"
+    kernels = [("k_count<512,false>+k_count<1024,false>" if tiered and os.environ.get("BIC_TIER0", "768") != "0" else
+                "k_count<512,false>" if c0_wide else "k_count<256,false>") +
                " (class 0: tables <= 2048 cells in shared memory, lane replicas for all but the largest)",
-               "k_count<512,false> (tables <= 12288 cells in shared memory)",
+               ("k_count<1024,false>+k_count<512,false>" if tiered and os.environ.get("BIC_TIER1", "3072") != "0" else "k_count<512,false>") +
+               " (class 1: tables <= 12288 cells in shared memory)",
                "k_count<1024,false> (tables <= 49152 cells in shared memory, one CTA per SM)",
                "k_count<1024,false,true> (tables > 49152 cells: shared-memory sub-range passes; k_count<256,true> L2 atomics "
                "when rows are few; k_count_cluster with BIC_CLUSTER=1)"]
