@@ -34,7 +34,7 @@ SYMBOLS = [
     "bic_set_dataset", "bic_count_families", "bic_score_families", "bic_score_dags_adj",
     "bic_score_dags_csr", "bic_score_dags_wire", "bic_cache_clear", "bic_cache_reserve",
     "bic_cache_stats", "bic_cache_export", "bic_cache_import", "bic_profile_enable", "bic_profile_reset", "bic_profile_get",
-    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy", "bic_comm_mode", "bic_plan_slices",
+    "bic_comm_unique_id", "bic_comm_init", "bic_comm_destroy", "bic_comm_mode", "bic_plan_slices", "bic_range_plan",
 ]
 
 
@@ -82,6 +82,20 @@ def plan_slices(N: int, n: int, families, sm_count: int = 148, tables_in_hbm: bo
     if rc != 0:
         raise BicError(rc, "bic_plan_slices: bad argument")
     return {"slices": list(out.slices), "ranged": bool(out.ranged), "passes": int(out.passes), "cluster": int(out.cluster)}
+
+
+def range_plan(cells: int, k: int, rad0: int, counters16: bool = False) -> dict:
+    """Sub-ranges of one class-3 family (host arithmetic only, works without a GPU): cells per
+    sub-range, passes over the rows, states of the first parent per pass (0: cut by cell index)."""
+    span, passes, ns = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    L = lib()
+    L.bic_range_plan.argtypes = [ctypes.c_uint32, ctypes.c_int32, ctypes.c_uint32, ctypes.c_int32,
+                                 ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+    L.bic_range_plan.restype = ctypes.c_int
+    rc = L.bic_range_plan(cells, k, rad0, int(counters16), ctypes.byref(span), ctypes.byref(passes), ctypes.byref(ns))
+    if rc != 0:
+        raise BicError(rc, "bic_range_plan: bad argument")
+    return {"span": span.value, "passes": passes.value, "states_per_pass": ns.value}
 
 
 class Profile(ctypes.Structure):

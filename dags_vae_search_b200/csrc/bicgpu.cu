@@ -1179,6 +1179,17 @@ int score_dags(bic_ctx *c, DagFormat fmt, const void *p0, const void *p1, int64_
 // ================================================================================ C ABI
 extern "C" {
 
+int bic_range_plan(uint32_t cells, int32_t k, uint32_t rad0, int32_t counters16, uint32_t *span, uint32_t *passes,
+                   uint32_t *states_per_pass) {
+    if (!span || !passes || !states_per_pass || cells == 0 || k < 0 || rad0 == 0) return BIC_ERR_ARG;
+    const RangePlan p = (counters16 && k <= 6) ? range_plan(cells, k, rad0, 2u * CLASS2_CELLS, false)
+                                               : range_plan(cells, k, rad0, CLASS2_CELLS, true);
+    *span = p.span;
+    *passes = p.passes;
+    *states_per_pass = p.ns;
+    return BIC_OK;
+}
+
 int bic_plan_slices(const bic_plan_in_t *in, bic_plan_out_t *out) {
     if (!in || !out || in->sm_count <= 0 || in->N <= 0 || in->n <= 0 || in->max_cells < 0) return BIC_ERR_ARG;
     for (int k = 0; k < NCLASS; ++k)

@@ -236,6 +236,14 @@ typedef struct {
                                 * many CTAs that share the table in distributed shared memory   */
 } bic_plan_out_t;
 int bic_plan_slices(const bic_plan_in_t *in, bic_plan_out_t *out);
+/* How one class-3 family (q*r = cells > 49152, k parents with more than one state, the first of
+ * them with rad0 states) is cut into the sub-ranges a CTA counts in shared memory: cells per
+ * sub-range, number of passes over the rows, and - when the sub-ranges follow the states of the
+ * first parent - the states per pass (else 0).  counters16 != 0: the 16-bit-counter variant
+ * (sub-ranges of twice the cells, k <= 6).  Host arithmetic shared with the kernels
+ * (range_plan, csrc/common.cuh). */
+int bic_range_plan(uint32_t cells, int32_t k, uint32_t rad0, int32_t counters16, uint32_t *span, uint32_t *passes,
+                   uint32_t *states_per_pass);
 
 /* ---- row sharding over several GPUs (one process per GPU) ------------------------------
  * Each rank holds N_rank rows of the same n columns.  After bic_comm_init every scoring call

@@ -257,6 +257,36 @@ def test_bench_workload_definitions():
 
 
 # ---------------------------------------------------------------- launch planning (no GPU)
+def test_class3_range_plan():
+    """How a table above one CTA's shared memory is cut into sub-ranges (range_plan in
+    csrc/common.cuh, shared by the kernels and exported as bic_range_plan): by cell index in steps
+    of 49 152 cells, or along the states of the first parent when the table below that parent has
+    at most 16 383 cells AND that needs no more passes; 16-bit counters double the sub-range."""
+    rp = nat.range_plan
+    # 21^4 cells (diabetes-shaped in-degree 3): 4 sub-ranges by cell index; along the first parent it would be 5 passes of <= 5 states
+    assert rp(194481, 3, 21) == {"span": 49152, "passes": 4, "states_per_pass": 0}
+    assert rp(194481, 3, 21, counters16=True) == {"span": 98304, "passes": 2, "states_per_pass": 0}
+    # 250 x 240: two passes either way -> runs of 125 states
+    assert rp(60000, 1, 250) == {"span": 30000, "passes": 2, "states_per_pass": 125}
+    assert rp(105000, 2, 250) == {"span": 35280, "passes": 3, "states_per_pass": 84}
+    assert rp(50400, 4, 21) == {"span": 26400, "passes": 2, "states_per_pass": 11}
+    assert rp(201600, 5, 21) == {"span": 48000, "passes": 5, "states_per_pass": 5}
+    # 100 800 cells below a 3-state first parent: too large for 16-bit lanes, cut by cell index
+    assert rp(302400, 6, 3) == {"span": 49152, "passes": 7, "states_per_pass": 0}
+    # more than six parents: the generic row loop, 32-bit counters even in the 16-bit variant
+    assert rp(177147, 10, 3) == {"span": 49152, "passes": 4, "states_per_pass": 0}
+    assert rp(177147, 10, 3, counters16=True) == {"span": 49152, "passes": 4, "states_per_pass": 0}
+    # every plan covers the table exactly once
+    for cells, k, rad0 in [(194481, 3, 21), (60000, 1, 250), (279300, 4, 20), (55860, 3, 21), (4000000, 3, 250)]:
+        for c16 in (False, True):
+            p = rp(cells, k, rad0, counters16=c16)
+            assert (p["passes"] - 1) * p["span"] < cells <= p["passes"] * p["span"]
+            if p["states_per_pass"]:
+                assert p["span"] == p["states_per_pass"] * (cells // rad0) and p["span"] <= 49152
+    with pytest.raises(nat.BicError):
+        rp(0, 1, 2)
+
+
 def test_launch_plan_rules(monkeypatch):
     """bic_plan_slices is the host arithmetic the library uses to cut a batch of new families into
     count-kernel work items (csrc/bicgpu.cu:plan_count).  It never changes a result, only the time,
